@@ -1,0 +1,148 @@
+"""Pin the oracle (oracle/) against fixtures produced by the REAL reference (tests/golden/gen_golden.py)
+and against itself (numpy statement vs plain-C statement).  CPU only."""
+import numpy as np
+import pytest
+import torch as t
+
+from oracle import cref, envs as oenvs, ppo as oppo, vec as ovec
+
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1"}
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize])
+
+
+@pytest.mark.parametrize("key", list(ENVS))
+def test_numpy_worker_matches_reference_worker(golden, key):
+    """oracle.vec.worker + oracle.envs == reference AsyncPPO.worker over the same env objects."""
+    g = golden("rollout_" + key)
+    E, T = int(g["E"]), int(g["T"])
+    vec = ovec.Vectorizer(oenvs.make(ENVS[key], max_episode_steps=T), E)
+    for i in range(E):
+        vec.envs[i].inject_state(g["init_state"][i])
+    tape, step = g["tape"], [0]
+
+    def act(states):
+        a = tape[step[0]][~vec.envs_active]
+        step[0] += 1
+        return a
+
+    mem = ovec.FlatMemory()
+    rs, ss = ovec.worker(vec, ovec.PerEnvMemory(E), act, mem)
+    assert ss == int(g["step_score"]) and float(rs) == float(g["reward_score"])
+    for name in ("states", "actions", "rewards", "dones"):
+        assert np.array_equal(bits(np.array(getattr(mem, name), np.float32)), bits(g[name])), name
+
+
+@pytest.mark.parametrize("key", list(ENVS))
+def test_c_rollout_matches_reference_worker(golden, key):
+    """plain-C orc_rollout == reference flat buffer, bit for bit (states, actions, rewards, dones)."""
+    g = golden("rollout_" + key)
+    E, T = int(g["E"]), int(g["T"])
+    tape = np.zeros((T,) + g["tape"].shape[1:], g["tape"].dtype)
+    tape[: len(g["tape"])] = g["tape"]
+    r = cref.rollout(ENVS[key], g["init_state"], tape, T)
+    assert r["N"] == len(g["states"]) == int(g["step_score"])
+    assert np.array_equal(bits(r["states"]), bits(g["states"]))
+    assert np.array_equal(bits(r["actions"].reshape(g["actions"].shape)), bits(g["actions"]))
+    assert np.array_equal(bits(r["rewards"]), bits(g["rewards"]))
+    assert np.array_equal(bits(r["dones"]), bits(g["dones"]))
+    assert np.array_equal(bits(r["final_state"]), bits(g["final_state"]))
+    assert r["reward_sum"] == pytest.approx(float(g["reward_score"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("env_id", list(ENVS.values()))
+def test_c_env_step_equals_numpy_env_step(env_id):
+    """Every fp64 state bit, f32 obs bit and fp64 reward bit agree between the two statements."""
+    rng = np.random.default_rng(5)
+    d = cref.env_dims(env_id)
+    n = 0
+    for ep in range(30):
+        e = oenvs.make(env_id, max_episode_steps=150)
+        e.reset(seed=100 + ep)
+        st = np.array(e.state, np.float64).copy()
+        while True:
+            a = (2.6 * np.tanh(rng.standard_normal(1))).astype(np.float32) if d["continuous"] else int(rng.integers(0, d["A"]))
+            o, r, term, trunc, _ = e.step(a)
+            o2, r2, term2 = cref.env_step(env_id, st, a)
+            assert np.array_equal(bits(o), bits(o2)) and np.float64(r).tobytes() == np.float64(r2).tobytes()
+            assert term == term2 and np.array_equal(bits(np.asarray(e.state, np.float64)), bits(st))
+            n += 1
+            if term or trunc:
+                break
+    assert n > 300, n
+
+
+def test_utils_match_reference(golden):
+    g = golden("utils")
+    mask = g["mask"].copy()
+    assert np.array_equal(ovec.indexes_of_active(len(mask), mask), g["indexes"])
+    assert ovec.number_of_active(mask) == int(g["number"])
+    assert np.array_equal(ovec.range_of_active(mask), g["range"])
+    assert np.array_equal(ovec.states_dropout(g["states"], g["dones"]), g["dropout"])
+    out = ovec.update_mask(mask, g["dones"])
+    assert out is mask and np.array_equal(mask, g["mask_after"])
+    E = len(mask)
+    buf, mem = ovec.PerEnvMemory(E), ovec.FlatMemory()
+    for i in range(int(g["ba_nsteps"])):
+        ovec.buffer_append(buf, g[f"ba_s{i}"], g[f"ba_a{i}"], g[f"ba_r{i}"], g[f"ba_d{i}"], g[f"ba_m{i}"], E)
+    ovec.transfer(buf, mem)
+    for name in ("states", "actions", "rewards", "dones"):
+        assert np.array_equal(bits(np.array(getattr(mem, name), np.float32)), bits(g["ba_" + name])), name
+
+
+LEARN = [("discrete", "cartpole"), ("continuous", "pendulum"), ("rnd", "acrobot"),
+         ("discrete_1step", "cartpole"), ("continuous_1step", "pendulum")]
+
+
+@pytest.mark.parametrize("name,roll", LEARN)
+def test_ppo_restatement_matches_reference_learn(golden, name, roll):
+    t.set_num_threads(1)
+    g, r = golden("learn_" + name), golden("rollout_" + roll)
+    cont, O, A = bool(g["is_continuous"]), int(g["O"]), int(g["A"])
+    p = oppo.unflatten(g["init_flat"], cont, O, A)
+    for k in oppo.param_keys(cont):
+        assert np.array_equal(p[k].numpy(), g["init." + k])
+    s, a = t.from_numpy(r["states"]), t.from_numpy(r["actions"])
+    with t.no_grad():
+        lp, v, ent = oppo.evaluate(p, cont, s, a)
+    np.testing.assert_allclose(lp.numpy(), g["eval_logp"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(v.numpy(), g["eval_value"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(float(ent), float(g["eval_entropy"]), rtol=1e-6)
+    rp = None
+    if bool(g["use_rnd"]):
+        rp = {k[len("rnd_init."):]: t.from_numpy(g[k]).clone() for k in g.files if k.startswith("rnd_init.")}
+        np.testing.assert_allclose(oppo.rnd_intrinsic(rp, s, 0.001).numpy(), g["rnd_intrinsic"], rtol=1e-6)
+    tr = {}
+    oppo.learn(p, cont, {k: r[k] for k in ("states", "actions", "rewards", "dones")}, lr=float(g["lr"]),
+               k_epochs=int(g["k_epochs"]), policy_clip=float(g["policy_clip"]), gae_lambda=float(g["GAE_lambda"]),
+               gamma=float(g["gamma"]), mini_batch_size=int(g["mini_batch_size"]), rnd_params=rp, trace=tr)
+    assert np.array_equal(bits(tr["returns"]), bits(g["gae_returns"]))  # float32 GAE is bit-exact
+    np.testing.assert_allclose(tr["advantages"], g["advantages"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(oppo.flatten(p, cont).numpy(), g["post_flat"], rtol=1e-5, atol=1e-6)
+    if rp is not None:
+        for k in oppo.RND_KEYS:
+            np.testing.assert_allclose(rp["pred_net." + k].numpy(), g["rnd_post.pred_net." + k], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["discrete", "continuous", "rnd"])
+def test_c_gae_matches_reference_compute_gae(golden, name):
+    g = golden("learn_" + name)
+    out = cref.gae(g["gae_rewards"], g["gae_dones"], g["gae_values"], g["gae_next_value"], float(g["gamma"]), float(g["GAE_lambda"]))
+    assert np.array_equal(bits(out), bits(g["gae_returns"]))
+    out2 = oppo.compute_gae(g["gae_rewards"], g["gae_dones"], g["gae_values"], g["gae_next_value"], float(g["gamma"]), float(g["GAE_lambda"]))
+    assert np.array_equal(bits(out2), bits(g["gae_returns"]))
+    adv, _, _ = cref.adv_norm(g["gae_returns"], g["gae_values"])
+    np.testing.assert_allclose(adv, g["advantages"], rtol=1e-5, atol=1e-6)
+
+
+def test_gae_without_terminal_done_bootstraps_last_value():
+    """PPO.py:187-188: a hand-filled buffer not ending in done=1 bootstraps from V(s_last)."""
+    rng = np.random.default_rng(3)
+    r, v = rng.standard_normal(50).astype(np.float32), rng.standard_normal(50).astype(np.float32)
+    d = np.zeros(50, np.float32); d[17] = 1
+    a = cref.gae(r, d, v, v[-1], 0.995, 0.95)
+    b = oppo.compute_gae(r, d, v, v[-1], 0.995, 0.95)
+    assert np.array_equal(bits(a), bits(b))
