@@ -1,0 +1,158 @@
+/*
+ * prl_b200 - C ABI of the B200-native data-parallel PPO hot path.
+ *
+ * Drop-in boundary for Raven4567/Parallel-Reinforcement-Learning.  The reference has no FFI of its own:
+ * its boundary is the Python API (PPO/, AsyncTools/), so these are the entry points a ctypes binding in
+ * the reference's Python would call; each one names the reference code it replaces (file:line under the
+ * reference repo).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (cudaMalloc'd / torch CUDA tensor .data_ptr()) unless its name ends
+ *     in `_host`; sizes are element counts; `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = ok, negative = error (PRL_ERR_*); prl_last_error() has the message (thread-local).
+ *   - no global state, no allocation inside the library; scratch memory is passed in as `ws`
+ *     (prl_scan_ws_bytes / prl_update_ws_floats tell how much).  Calls are asynchronous on `stream`.
+ *   - layouts: env state is SoA fp64 [S][E]; the rollout buffer is time-major [T][C][E] float32;
+ *     PPO.memory is env-major flat: states [N][O], actions [N] or [N][A], rewards [N], dones [N] float32;
+ *     network parameters are ONE flat float32 buffer in torch `.parameters()` order (prl_policy_param_count).
+ */
+#ifndef PRL_B200_H
+#define PRL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_VERSION 100
+
+enum { PRL_OK = 0, PRL_ERR_INVALID = -1, PRL_ERR_CUDA = -2, PRL_ERR_CAPACITY = -3 };
+enum { PRL_ENV_CARTPOLE = 0, PRL_ENV_PENDULUM = 1, PRL_ENV_ACROBOT = 2 };
+enum { PRL_ACT_I32 = 0, PRL_ACT_I64 = 1, PRL_ACT_F32 = 2 };
+
+const char *prl_last_error(void);
+int prl_version(void);
+
+/* gym.make(id) facts the reference reads from env.observation_space / action_space (train.py:12-13). */
+int prl_env_info(int env_id, int *state_dim, int *obs_dim, int *action_dim, int *is_continuous, int *max_episode_steps);
+/* number of float32 in ActorCritic(is_continuous, O, A).parameters()  (PPO/ActorCritic.py:14-64) */
+int64_t prl_policy_param_count(int is_continuous, int obs_dim, int action_dim);
+/* number of float32 in ONE of RND's two nets (PPO/RND.py:25-31) */
+int64_t prl_rnd_param_count(int in_features, int out_features);
+size_t prl_scan_ws_bytes(int64_t n);
+
+/* ---------------------------------------------------------------- test hooks (parity tests only) */
+int prl_test_sincos(const double *x, double *sin_out, double *cos_out, int64_t n, void *stream);
+int prl_test_pow2(const double *x, double *out, const float *xf, float *outf, int64_t n, void *stream);
+int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
+
+/* ---------------------------------------------------------------- EnvVectorizer (AsyncTools/AsyncPPO.py:35-102) */
+/* reset(): AsyncPPO.py:48-62.  Draws every env's start state from Philox(seed, episode) in the env's reset box,
+ * zeroes the TimeLimit counters and the terminal mask, writes obs [E][O] float32. */
+int prl_env_reset(int env_id, int E, uint64_t seed, uint64_t episode, double *state, int32_t *elapsed,
+                  uint8_t *terminal, float *obs, void *stream);
+/* reset() with injected start states (teacher forcing): state_aos is [E][S] fp64. */
+int prl_env_set_state(int env_id, int E, const double *state_aos, double *state, int32_t *elapsed,
+                      uint8_t *terminal, float *obs, void *stream);
+int prl_env_get_state(int env_id, int E, const double *state, double *state_aos, void *stream);
+/* step(actions): AsyncPPO.py:64-102.  Steps the n non-terminal envs active_idx[0..n) (ascending env index) with
+ * the compact actions[rank]; returns compact next obs [n][O] f32, rewards [n] f64, dones/truncs [n] u8.
+ * TimeLimit: elapsed += 1; trunc = elapsed >= max_episode_steps. */
+int prl_env_step(int env_id, int E, int n, const int32_t *active_idx, const void *actions, int action_dtype,
+                 double *state, int32_t *elapsed, int max_episode_steps, float *obs, double *rewards,
+                 uint8_t *dones, uint8_t *truncs, void *stream);
+
+/* ---------------------------------------------------------------- AsyncTools/utils.py */
+/* indexes_of_active_environments (utils.py:3-4) + number_of_active_environments (:6-7): idx = arange(E)[~terminal],
+ * *count = len(idx).  Generic form: select where flags[i] == want. */
+int prl_compact_indices(const uint8_t *flags, int64_t n, int want, int32_t *idx, int32_t *count, void *ws,
+                        size_t ws_bytes, void *stream);
+/* inactive_states_dropout (utils.py:14-15): out = rows[idx] for a compacted idx; rows are `width` float32 wide. */
+int prl_gather_rows(const float *rows, const int32_t *idx, const int32_t *count, int64_t max_rows, int width,
+                    float *out, void *stream);
+/* update_active_environments_list (utils.py:38-43): terminal[active_idx[i]] = dones[i]. */
+int prl_mask_update(uint8_t *terminal, const int32_t *active_idx, const uint8_t *dones, int n, void *stream);
+/* buffer_append (utils.py:17-36) into the device VecMemory (AsyncPPO.py:11-33): for rank i, env e = active_idx[i]:
+ * slot t = lengths[e]; buf_*[t][.][e] = float32(item[i]); lengths[e] = t + 1.  Returns PRL_ERR_CAPACITY via
+ * *overflow != 0 (device flag) when t >= T_cap. */
+int prl_buffer_append(int E, int T_cap, int n, const int32_t *active_idx, const float *states, int obs_dim,
+                      const float *actions, int act_width, const float *rewards, const float *dones,
+                      float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones,
+                      int32_t *lengths, int32_t *overflow, void *stream);
+/* buffer_to_target_buffer_transfer (utils.py:45-50): env-major, time-minor concatenation of the per-env
+ * episodes behind the `base` items already in PPO.memory; zeroes lengths (buffer.clear()).  *total (device int64)
+ * = base + sum(lengths). */
+int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const float *buf_states,
+                        const float *buf_actions, const float *buf_rewards, const float *buf_dones,
+                        int32_t *lengths, int64_t base, int64_t capacity, float *mem_states, float *mem_actions,
+                        float *mem_rewards, float *mem_dones, int64_t *total, void *ws, size_t ws_bytes,
+                        void *stream);
+
+/* ---------------------------------------------------------------- PPO.get_action (PPO/PPO.py:82-96) */
+/* states [n][O] f32 -> sampled actions: discrete int64 [n] (Categorical(probs).sample()), continuous f32 [n][A]
+ * (tanh(mu + std*eps) * action_scaling).  Randomness: Philox(seed; row id, call_index) where row id = row_ids[i] (the
+ * env index of compact row i; NULL -> i), so a step-by-step loop with call_index = (episode << 32) | t draws the
+ * same numbers as the fused prl_rollout.  Optional output (may be NULL): dist [n][A] probs or [n][2A] (mu, std). */
+int prl_policy_act(const float *params, int is_continuous, int obs_dim, int action_dim, float action_scaling,
+                   const float *states, const int32_t *row_ids, int64_t n, uint64_t seed, uint64_t call_index,
+                   void *actions, float *dist, void *stream);
+/* ActorCritic.get_evaluate (PPO/ActorCritic.py:118-146) forward: logp [n], value [n], entropy_sum (device double,
+ * ACCUMULATED: caller zeroes it; mean = sum / n). */
+int prl_policy_evaluate(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
+                        const float *actions, int64_t n, float *logp, float *value, double *entropy_sum,
+                        void *stream);
+
+/* ---------------------------------------------------------------- AsyncPPO.worker (AsyncPPO.py:117-146), fused */
+/* One episode per env in ONE launch: obs -> policy forward -> sample -> physics -> TimeLimit -> buffer write, looped
+ * until done|trunc, at most T_cap (= max_episode_steps) steps.  tape != NULL replaces the sampler with taped actions
+ * tape[t][e] (int32) / tape[t][e][A] (f32) - teacher forcing.  Outputs: time-major buffer, lengths, final state,
+ * terminal mask (all 1), scores[0] = sum of rewards (f64), scores[1] = number of env steps (as f64). */
+int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed,
+                uint64_t episode, const void *tape, double *state, int32_t *elapsed, uint8_t *terminal,
+                float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones, int32_t *lengths,
+                double *scores, void *stream);
+
+/* ---------------------------------------------------------------- PPO.compute_gae (PPO/PPO.py:107-120) */
+/* Flat reverse scan over the env-major buffer, float32, same operation order as the reference;
+ * next_value = values[N-1] as in PPO.py:188 when next_value_ptr == NULL. */
+int prl_gae(const float *rewards, const float *dones, const float *values, const float *next_value_ptr,
+            double gamma, double gae_lambda, int64_t N, float *returns, void *ws, size_t ws_bytes, void *stream);
+size_t prl_gae_ws_bytes(int64_t N);
+/* Column form on the time-major rollout buffer [T][E] (each env's episode scanned backwards from lengths[e]-1). */
+int prl_gae_columns(const float *rewards, const float *dones, const float *values, const int32_t *lengths, int E,
+                    int T_cap, double gamma, double gae_lambda, float *returns, void *stream);
+/* PPO.py:198-199: adv = returns - values; (adv - mean) / (std_unbiased + 1e-8).  stats (device double[4]) receives
+ * {sum, sum of squared deviations, count, unused}; pass stats_in to normalise with externally reduced statistics
+ * (multi-GPU: allreduce of stats between the two phases). phase 1 = statistics, 2 = normalise, 3 = both. */
+int prl_adv_normalize(const float *returns, const float *values, int64_t N, float *adv, double *stats, int phase,
+                      void *stream);
+
+/* ---------------------------------------------------------------- PPO.learn minibatch step (PPO/PPO.py:219-252) */
+size_t prl_update_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch);
+/* forward + clipped-surrogate/SmoothL1/entropy loss + backward for ONE minibatch of b rows; writes the flat
+ * gradient of loss.mean() (same layout as params) and loss_out = {sum of per-row policy terms, sum of SmoothL1
+ * terms, sum of entropies, b} as device doubles.  inv_count = 1 / (global minibatch rows) so that sharded
+ * minibatches sum to the global mean gradient. */
+int prl_ppo_grad(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
+                 const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
+                 float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
+                 void *stream);
+/* nn.utils.clip_grad_norm_(params, max_norm) + AdamW.step (PPO.py:250-252; torch defaults betas (0.9,0.999),
+ * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
+int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,
+                   float lr, float weight_decay, float max_norm, double *grad_norm_out, void *stream);
+
+/* ---------------------------------------------------------------- RND (PPO/RND.py:71-115) */
+/* compute_intrinsic_reward: out[i] = beta * || pred(s_i) - target(s_i) ||_2 ; add_to != NULL: out = add_to + that */
+int prl_rnd_intrinsic(const float *target_params, const float *pred_params, int in_features, int out_features,
+                      const float *states, int64_t n, float beta, const float *add_to, float *out, void *stream);
+/* update_pred for one chunk: gradient of MSELoss(mean) wrt pred_params (flat), loss_out[0] += sum of squared err */
+int prl_rnd_grad(const float *target_params, const float *pred_params, int in_features, int out_features,
+                 const float *states, int64_t n, float *grad, double *loss_out, float *ws, size_t ws_floats,
+                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRL_B200_H */

@@ -1,0 +1,131 @@
+"""PPO.memory: the flat transition store `learn()` consumes (reference: /root/reference/PPO/Memory.py:7-30).
+
+Same surface as the reference - `.states/.actions/.rewards/.dones` behave like Python lists of float32 items, `push`,
+`clear` - but transitions that arrive from the device rollout buffer stay in HBM as flat env-major tensors
+(states [N][O], actions [N][AW], rewards [N], dones [N]); host items are only materialised if somebody indexes them.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+FIELDS = ("states", "actions", "rewards", "dones")
+
+
+class _Field:
+    """List-like view of one field: host items (pushed / `+=`-ed by user code) followed by device rows."""
+
+    def __init__(self, owner, name):
+        self._owner, self._name, self._host = owner, name, []
+
+    def __len__(self):
+        return len(self._host) + self._owner._dev_count
+
+    def append(self, item):
+        self._owner._host_after_device()
+        self._host.append(item)
+
+    def extend(self, items):
+        for it in items:
+            self.append(it)
+
+    def __iadd__(self, items):
+        self.extend(items)
+        return self
+
+    def _rows(self):
+        out = list(self._host)
+        t = self._owner._dev.get(self._name)
+        if t is not None and self._owner._dev_count:
+            arr = t[: self._owner._dev_count].cpu().numpy()
+            if arr.ndim == 2 and arr.shape[1] == 1 and self._name == "actions" and self._owner._scalar_actions:
+                arr = arr[:, 0]
+            out.extend(list(arr))
+        return out
+
+    def __iter__(self):
+        return iter(self._rows())
+
+    def __getitem__(self, i):
+        return self._rows()[i]
+
+    def __delitem__(self, i):
+        if i == slice(None, None, None):
+            self._host.clear()
+        else:
+            raise TypeError("only `del field[:]` is supported")
+
+    def clear(self):
+        self._host.clear()
+
+    def __repr__(self):
+        return f"<{self._name}: {len(self)} items>"
+
+
+class Memory:
+    def __init__(self):
+        self._dev = {}
+        self._dev_count = 0
+        self._dev_cap = 0
+        self._scalar_actions = True
+        self._total = None  # device int64 scratch written by the transfer kernel
+        self._fields = {n: _Field(self, n) for n in FIELDS}
+
+    # list-like attributes, assignable like the reference's plain lists
+    states = property(lambda s: s._fields["states"], lambda s, v: s._assign("states", v))
+    actions = property(lambda s: s._fields["actions"], lambda s, v: s._assign("actions", v))
+    rewards = property(lambda s: s._fields["rewards"], lambda s, v: s._assign("rewards", v))
+    dones = property(lambda s: s._fields["dones"], lambda s, v: s._assign("dones", v))
+
+    def _assign(self, name, value):
+        if value is self._fields[name]:
+            return  # `mem.states += [...]` re-assigns the same object
+        self._fields[name]._host = list(value)
+
+    def _host_after_device(self):
+        if self._dev_count:
+            raise RuntimeError("mixing host pushes after a device transfer is not supported; call learn() or clear() first")
+
+    def push(self, state, action, reward, done):
+        """Memory.py:14-24: every item is stored as float32."""
+        for name, x in zip(FIELDS, (state, action, reward, done)):
+            self._fields[name].append(np.asarray(x).astype(np.float32))
+
+    def clear(self):
+        for f in self._fields.values():
+            f.clear()
+        self._dev_count = 0
+
+    # ---- device side -------------------------------------------------------------------------------------------
+    def reserve(self, capacity, obs_dim, act_width, device):
+        """Make room for `capacity` rows in HBM, keeping what is already there."""
+        if self._dev and self._dev_cap >= capacity and self._dev["states"].shape[1] == obs_dim:
+            return
+        new = {"states": torch.empty(capacity, obs_dim, dtype=torch.float32, device=device),
+               "actions": torch.empty(capacity, act_width, dtype=torch.float32, device=device),
+               "rewards": torch.empty(capacity, dtype=torch.float32, device=device),
+               "dones": torch.empty(capacity, dtype=torch.float32, device=device)}
+        if self._dev and self._dev_count:
+            for k in FIELDS:
+                new[k][: self._dev_count] = self._dev[k][: self._dev_count]
+        self._dev, self._dev_cap = new, capacity
+        if self._total is None:
+            self._total = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def device_view(self, obs_dim, act_width, device):
+        """(states [N][O], actions [N][AW], rewards [N], dones [N]) on the device, host items uploaded first."""
+        nh = len(self._fields["states"]._host)
+        if nh:
+            host = {k: np.array(self._fields[k]._host, dtype=np.float32) for k in FIELDS}
+            N = nh + self._dev_count
+            if self._dev_count:
+                raise RuntimeError("host items and device rows cannot be combined")
+            s = torch.from_numpy(host["states"].reshape(N, obs_dim)).to(device)
+            a = torch.from_numpy(host["actions"].reshape(N, -1)).to(device)
+            if a.shape[1] != act_width:
+                a = a[:, :act_width].contiguous()
+            r = torch.from_numpy(host["rewards"].reshape(N)).to(device)
+            d = torch.from_numpy(host["dones"].reshape(N)).to(device)
+            return s, a, r, d
+        n = self._dev_count
+        return tuple(self._dev[k][:n] for k in FIELDS)

@@ -1,0 +1,546 @@
+// Rollout half of the hot path: vectorised env reset/step, active-mask bookkeeping (stream compaction), the
+// device-resident VecMemory, PPO.get_action, and the fused one-launch AsyncPPO.worker.
+//
+// Reference: /root/reference/AsyncTools/AsyncPPO.py:11-146, AsyncTools/utils.py:1-50, PPO/PPO.py:82-96.
+#include "envs.cuh"
+#include "policy.cuh"
+
+namespace prl {
+
+constexpr int TPB = 128;  // threads per block for the one-env-per-thread kernels
+
+// ------------------------------------------------------------------------------------------------ state access
+template <class ENV>
+__device__ __forceinline__ void load_state(const double *__restrict__ state, int E, int e, double (&s)[ENV::S]) {
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) s[i] = state[(size_t)i * E + e];
+}
+template <class ENV>
+__device__ __forceinline__ void store_state(double *__restrict__ state, int E, int e, const double (&s)[ENV::S]) {
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) state[(size_t)i * E + e] = s[i];
+}
+template <class ENV>
+__device__ __forceinline__ void store_obs_row(float *__restrict__ obs, size_t row, const float (&o)[ENV::O]) {
+    if constexpr (ENV::O == 4) {
+        reinterpret_cast<float4 *>(obs)[row] = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < ENV::O; ++i) obs[row * ENV::O + i] = o[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reset
+template <class ENV>
+__global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__restrict__ state,
+                            int32_t *__restrict__ elapsed, uint8_t *__restrict__ terminal, float *__restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Philox ph(seed);
+    double s[ENV::S];
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) {
+        if ((i & 1) == 0) ph((uint32_t)e, (uint32_t)episode, (STREAM_RESET << 24) | (uint32_t)(i >> 1), (uint32_t)(episode >> 32), r);
+        const double u = u01d(r[2 * (i & 1)], r[2 * (i & 1) + 1]);
+        // numpy Generator.uniform: low + (high - low) * u
+        const double hi = ENV::reset_hi(i), lo = -hi;
+        double v = dadd(lo, dmul(dsub(hi, lo), u));
+        if (ENV::RESET_F32) v = (double)(float)v;
+        s[i] = v;
+    }
+    store_state<ENV>(state, E, e, s);
+    elapsed[e] = 0;
+    terminal[e] = 0;
+    float o[ENV::O];
+    ENV::obs(s, o);
+    store_obs_row<ENV>(obs, e, o);
+}
+
+template <class ENV>
+__global__ void k_env_set_state(int E, const double *__restrict__ aos, double *__restrict__ state,
+                                int32_t *__restrict__ elapsed, uint8_t *__restrict__ terminal, float *__restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    double s[ENV::S];
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) s[i] = aos[(size_t)e * ENV::S + i];
+    store_state<ENV>(state, E, e, s);
+    elapsed[e] = 0;
+    terminal[e] = 0;
+    float o[ENV::O];
+    ENV::obs(s, o);
+    store_obs_row<ENV>(obs, e, o);
+}
+
+template <class ENV>
+__global__ void k_env_get_state(int E, const double *__restrict__ state, double *__restrict__ aos) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) aos[(size_t)e * ENV::S + i] = state[(size_t)i * E + e];
+}
+
+// ------------------------------------------------------------------------------------------------ compact step
+template <class ENV, int ADT>
+__global__ void k_env_step(int E, int n, const int32_t *__restrict__ active_idx, const void *__restrict__ actions,
+                           double *__restrict__ state, int32_t *__restrict__ elapsed, int max_steps,
+                           float *__restrict__ obs, double *__restrict__ rewards, uint8_t *__restrict__ dones,
+                           uint8_t *__restrict__ truncs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = active_idx[i];
+    double s[ENV::S];
+    load_state<ENV>(state, E, e, s);
+    typename ENV::Action a;
+    if constexpr (ENV::CONT) a = static_cast<const float *>(actions)[(size_t)i * ENV::A];
+    else if constexpr (ADT == PRL_ACT_I64) a = (int)static_cast<const int64_t *>(actions)[i];
+    else a = static_cast<const int32_t *>(actions)[i];
+    double r;
+    const bool term = ENV::step(s, a, r);
+    store_state<ENV>(state, E, e, s);
+    const int el = elapsed[e] + 1;
+    elapsed[e] = el;
+    float o[ENV::O];
+    ENV::obs(s, o);
+    store_obs_row<ENV>(obs, i, o);
+    rewards[i] = r;
+    dones[i] = term;
+    truncs[i] = el >= max_steps;
+}
+
+// ------------------------------------------------------------------------------------------------ stream compaction
+// Two launches: per-block counts, then (block offset = sum of earlier counts) + warp-ballot ranks.  Output order is
+// ascending index, as numpy boolean indexing gives (utils.py:4, :15).
+constexpr int SCAN_TPB = 1024;
+
+__global__ void k_flag_counts(const uint8_t *__restrict__ flags, int64_t n, int want, int32_t *__restrict__ counts) {
+    __shared__ int32_t sc[32];
+    const int64_t i = (int64_t)blockIdx.x * SCAN_TPB + threadIdx.x;
+    const int f = (i < n) && ((flags[i] != 0) == (want != 0));
+    const int c = block_sum<int32_t>(f, sc);
+    if (threadIdx.x == 0) counts[blockIdx.x] = c;
+}
+
+__device__ __forceinline__ int64_t block_prefix_of_counts(const int32_t *__restrict__ counts, int b, int64_t *sc) {
+    int64_t part = 0;
+    for (int j = threadIdx.x; j < b; j += blockDim.x) part += counts[j];
+    part = block_sum<int64_t>(part, sc);
+    __shared__ int64_t base;
+    if (threadIdx.x == 0) base = part;
+    __syncthreads();
+    return base;
+}
+
+__global__ void k_flag_compact(const uint8_t *__restrict__ flags, int64_t n, int want, const int32_t *__restrict__ counts,
+                               int32_t *__restrict__ idx, int32_t *__restrict__ count_out) {
+    __shared__ int64_t sc64[32];
+    __shared__ int32_t wsum[32];
+    const int64_t base = block_prefix_of_counts(counts, blockIdx.x, sc64);
+    const int64_t i = (int64_t)blockIdx.x * SCAN_TPB + threadIdx.x;
+    const int f = (i < n) && ((flags[i] != 0) == (want != 0));
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        wsum[lane] = incl - v;  // exclusive
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) *count_out = (int32_t)(base + incl);
+    }
+    __syncthreads();
+    if (f) idx[base + wsum[w] + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
+}
+
+__global__ void k_gather_rows(const float *__restrict__ rows, const int32_t *__restrict__ idx,
+                              const int32_t *__restrict__ count, int width, float *__restrict__ out) {
+    const int64_t total = (int64_t)(*count) * width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / width;
+        const int c = (int)(i - r * width);
+        out[i] = rows[(int64_t)idx[r] * width + c];
+    }
+}
+
+__global__ void k_mask_update(uint8_t *__restrict__ terminal, const int32_t *__restrict__ active_idx,
+                              const uint8_t *__restrict__ dones, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) terminal[active_idx[i]] = dones[i] != 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device VecMemory
+__global__ void k_buffer_append(int E, int T_cap, int n, const int32_t *__restrict__ active_idx,
+                                const float *__restrict__ states, int O, const float *__restrict__ actions, int AW,
+                                const float *__restrict__ rewards, const float *__restrict__ dones,
+                                float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
+                                float *__restrict__ bd, int32_t *__restrict__ lengths, int32_t *__restrict__ overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = active_idx[i];
+    const int t = lengths[e];
+    if (t >= T_cap) { atomicExch(overflow, 1); return; }
+    for (int c = 0; c < O; ++c) bs[((size_t)t * O + c) * E + e] = states[(size_t)i * O + c];
+    for (int c = 0; c < AW; ++c) ba[((size_t)t * AW + c) * E + e] = actions[(size_t)i * AW + c];
+    br[(size_t)t * E + e] = rewards[i];
+    bd[(size_t)t * E + e] = dones[i];
+    lengths[e] = t + 1;
+}
+
+// exclusive scan of int32 lengths -> int64 offsets (two launches, same structure as the compaction)
+__global__ void k_len_block_sums(const int32_t *__restrict__ len, int E, int32_t *__restrict__ sums) {
+    __shared__ int32_t sc[32];
+    const int e = blockIdx.x * SCAN_TPB + threadIdx.x;
+    const int c = block_sum<int32_t>(e < E ? len[e] : 0, sc);
+    if (threadIdx.x == 0) sums[blockIdx.x] = c;
+}
+
+__global__ void k_len_offsets(const int32_t *__restrict__ len, int E, const int32_t *__restrict__ sums, int64_t base0,
+                              int64_t *__restrict__ offsets, int64_t *__restrict__ total) {
+    __shared__ int64_t sc64[32];
+    __shared__ int32_t wsum[32];
+    const int64_t base = base0 + block_prefix_of_counts(sums, blockIdx.x, sc64);
+    const int e = blockIdx.x * SCAN_TPB + threadIdx.x;
+    const int v = e < E ? len[e] : 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int x = wsum[lane], in2 = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, in2, o);
+            if (lane >= o) in2 += t;
+        }
+        wsum[lane] = in2 - x;
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) *total = base + in2;
+    }
+    __syncthreads();
+    if (e < E) offsets[e] = base + wsum[w] + (incl - v);
+}
+
+// time-major [T][C][E] -> env-major flat [off[e] + t][C]: a warp transposes a 32(t) x 32(e) tile through shared
+// memory so that both the reads (along e) and the writes (along t) are contiguous.
+__global__ void k_transfer(int E, int T_cap, int C, const float *__restrict__ src, const int32_t *__restrict__ len,
+                           const int64_t *__restrict__ offsets, float *__restrict__ dst, int64_t capacity) {
+    __shared__ float tile[4][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e0 = (blockIdx.x * 4 + w) * 32;
+    if (e0 >= E) return;
+    const int e = e0 + lane;
+    const int my_len = e < E ? len[e] : 0;
+    int max_len = my_len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_len = max(max_len, __shfl_xor_sync(0xffffffffu, max_len, o));
+    const int64_t my_off = e < E ? offsets[e] : 0;
+    for (int c = 0; c < C; ++c) {
+        for (int t0 = 0; t0 < max_len; t0 += 32) {
+#pragma unroll 4
+            for (int tt = 0; tt < 32; ++tt) {
+                const int t = t0 + tt;
+                tile[w][tt][lane] = (t < my_len) ? src[((size_t)t * C + c) * E + e] : 0.f;
+            }
+            __syncwarp();
+            for (int ee = 0; ee < 32; ++ee) {
+                const int l = __shfl_sync(0xffffffffu, my_len, ee);
+                const int64_t off = __shfl_sync(0xffffffffu, my_off, ee);
+                const int t = t0 + lane;
+                if (t < l && off + t < capacity) dst[(off + t) * C + c] = tile[w][lane][ee];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_zero_i32(int32_t *p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ PPO.get_action
+__global__ void __launch_bounds__(TPB)
+k_policy_act(const float *__restrict__ params, PolicyLayout L, float action_scaling, const float *__restrict__ states,
+             const int32_t *__restrict__ row_ids, int64_t n, uint64_t seed, uint64_t call_index, void *__restrict__ actions,
+             float *__restrict__ dist) {
+    extern __shared__ __align__(16) float smem[];
+    const ActSmem W = stage_act_weights(smem, params, L);
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (row >= n) return;
+    float *col = W.scratch + threadIdx.x;
+    const float *x = states + row * L.O;
+    policy_forward(W, L.O, [&](int i) { return __ldg(x + i); }, col, TPB);
+    Philox ph(seed);
+    const uint32_t rid = row_ids ? (uint32_t)row_ids[row] : (uint32_t)row;
+    uint32_t r[4];
+    if (!L.cont) {
+        ph(rid, (uint32_t)call_index, action_stream_word(0), (uint32_t)(call_index >> 32), r);
+        const int a = sample_categorical(col, TPB, L.A, u01f(r[0]), dist ? dist + row * L.A : nullptr);
+        static_cast<int64_t *>(actions)[row] = a;
+    } else {
+        float *out = static_cast<float *>(actions) + row * L.A;
+        float nrm[4];
+        for (int a = 0; a < L.A; ++a) {
+            if ((a & 3) == 0) {
+                ph(rid, (uint32_t)call_index, action_stream_word(a >> 2), (uint32_t)(call_index >> 32), r);
+                normals4(r, nrm);
+            }
+            const float mu = col[(HID + a) * TPB];
+            const float ls = col[(HID + L.A + a) * TPB];
+            const float sd = softplus_t(fminf(fmaxf(ls, -2.f), 2.f));
+            const float tril = sqrtf(sd * sd);  // cholesky of diag(std^2)
+            out[a] = tanhf(fmaf(tril, nrm[a & 3], mu)) * action_scaling;
+            if (dist) { dist[row * 2 * L.A + a] = mu; dist[row * 2 * L.A + L.A + a] = tril; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused worker()
+template <class ENV, bool TAPED>
+__global__ void __launch_bounds__(TPB)
+k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, float action_scaling, uint64_t seed,
+          uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
+          uint8_t *__restrict__ terminal, float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
+          float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores) {
+    extern __shared__ __align__(16) float smem[];
+    ActSmem W{};
+    if constexpr (!TAPED) {
+        W = stage_act_weights(smem, params, L);
+        __syncthreads();
+    }
+    __shared__ double red[32];
+    const int e = blockIdx.x * TPB + threadIdx.x;
+    const bool valid = e < E;
+    bool alive = valid;
+    double s[ENV::S];
+    if (valid) load_state<ENV>(state, E, e, s);
+    double rsum = 0.0;
+    int len = 0;
+    Philox ph(seed);
+    float *col = TAPED ? nullptr : W.scratch + threadIdx.x;
+    for (int t = 0; t < T_cap; ++t) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+            float o[ENV::O];
+            ENV::obs(s, o);
+            typename ENV::Action a;
+            float a_store;
+            if constexpr (TAPED) {
+                if constexpr (ENV::CONT) a = static_cast<const float *>(tape)[((size_t)t * E + e) * ENV::A];
+                else a = static_cast<const int32_t *>(tape)[(size_t)t * E + e];
+                a_store = (float)a;
+            } else {
+                policy_forward(W, ENV::O, [&](int i) { return o[i]; }, col, TPB);
+                uint32_t r[4];
+                ph((uint32_t)e, (uint32_t)t, action_stream_word(0), (uint32_t)episode, r);
+                if constexpr (ENV::CONT) {
+                    float nrm[4];
+                    normals4(r, nrm);
+                    const float mu = col[HID * TPB];
+                    const float ls = col[(HID + ENV::A) * TPB];
+                    const float sd = softplus_t(fminf(fmaxf(ls, -2.f), 2.f));
+                    a = tanhf(fmaf(sqrtf(sd * sd), nrm[0], mu)) * action_scaling;
+                    a_store = a;
+                } else {
+                    a = sample_categorical(col, TPB, ENV::A, u01f(r[0]), nullptr);
+                    a_store = (float)a;
+                }
+            }
+            double r64;
+            const bool term = ENV::step(s, a, r64);
+            const bool fin = term || (t + 1 >= T_cap);
+#pragma unroll
+            for (int c = 0; c < ENV::O; ++c) bs[((size_t)t * ENV::O + c) * E + e] = o[c];
+            ba[(size_t)t * E + e] = a_store;
+            br[(size_t)t * E + e] = (float)r64;
+            bd[(size_t)t * E + e] = fin ? 1.f : 0.f;
+            rsum += r64;
+            len = t + 1;
+            alive = !fin;
+        }
+    }
+    if (valid) {
+        store_state<ENV>(state, E, e, s);
+        lengths[e] = len;
+        elapsed[e] = len;
+        terminal[e] = 1;
+    }
+    const double bsum = block_sum<double>(rsum, red);
+    const double blen = block_sum<double>((double)len, red);
+    if (threadIdx.x == 0) {
+        atomicAdd(scores + 0, bsum);
+        atomicAdd(scores + 1, blen);
+    }
+}
+
+}  // namespace prl
+
+// =================================================================================================== C ABI
+using namespace prl;
+
+extern "C" {
+
+int prl_env_reset(int env_id, int E, uint64_t seed, uint64_t episode, double *state, int32_t *elapsed,
+                  uint8_t *terminal, float *obs, void *stream) {
+    PRL_REQUIRE(E > 0 && state && elapsed && terminal && obs, "prl_env_reset: bad arguments (E=%d)", E);
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        k_env_reset<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, seed, episode, state, elapsed, terminal, obs);
+        return check_launch("k_env_reset");
+    });
+}
+
+int prl_env_set_state(int env_id, int E, const double *state_aos, double *state, int32_t *elapsed, uint8_t *terminal,
+                      float *obs, void *stream) {
+    PRL_REQUIRE(E > 0 && state_aos && state && elapsed && terminal && obs, "prl_env_set_state: bad arguments");
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        k_env_set_state<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, state_aos, state, elapsed, terminal, obs);
+        return check_launch("k_env_set_state");
+    });
+}
+
+int prl_env_get_state(int env_id, int E, const double *state, double *state_aos, void *stream) {
+    PRL_REQUIRE(E > 0 && state && state_aos, "prl_env_get_state: bad arguments");
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        k_env_get_state<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, state, state_aos);
+        return check_launch("k_env_get_state");
+    });
+}
+
+int prl_env_step(int env_id, int E, int n, const int32_t *active_idx, const void *actions, int action_dtype,
+                 double *state, int32_t *elapsed, int max_episode_steps, float *obs, double *rewards, uint8_t *dones,
+                 uint8_t *truncs, void *stream) {
+    PRL_REQUIRE(E > 0 && n >= 0 && n <= E, "prl_env_step: n=%d out of range for E=%d", n, E);
+    if (n == 0) return PRL_OK;
+    PRL_REQUIRE(active_idx && actions && state && elapsed && obs && rewards && dones && truncs, "prl_env_step: null pointer");
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (ENV::CONT) {
+            PRL_REQUIRE(action_dtype == PRL_ACT_F32, "prl_env_step: continuous env needs float32 actions");
+            k_env_step<ENV, PRL_ACT_F32><<<cdiv(n, TPB), TPB, 0, st>>>(E, n, active_idx, actions, state, elapsed, max_episode_steps, obs, rewards, dones, truncs);
+        } else if (action_dtype == PRL_ACT_I64) {
+            k_env_step<ENV, PRL_ACT_I64><<<cdiv(n, TPB), TPB, 0, st>>>(E, n, active_idx, actions, state, elapsed, max_episode_steps, obs, rewards, dones, truncs);
+        } else {
+            PRL_REQUIRE(action_dtype == PRL_ACT_I32, "prl_env_step: discrete env needs int32/int64 actions");
+            k_env_step<ENV, PRL_ACT_I32><<<cdiv(n, TPB), TPB, 0, st>>>(E, n, active_idx, actions, state, elapsed, max_episode_steps, obs, rewards, dones, truncs);
+        }
+        return check_launch("k_env_step");
+    });
+}
+
+size_t prl_scan_ws_bytes(int64_t n) { return (size_t)(cdiv(n, SCAN_TPB) + 1) * sizeof(int32_t) + (size_t)(n + 1) * sizeof(int64_t); }
+
+int prl_compact_indices(const uint8_t *flags, int64_t n, int want, int32_t *idx, int32_t *count, void *ws, size_t ws_bytes,
+                        void *stream) {
+    PRL_REQUIRE(n >= 0 && count, "prl_compact_indices: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { PRL_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st)); return PRL_OK; }
+    const int nb = cdiv(n, SCAN_TPB);
+    PRL_REQUIRE(flags && idx && ws && ws_bytes >= (size_t)nb * sizeof(int32_t), "prl_compact_indices: workspace too small");
+    int32_t *counts = static_cast<int32_t *>(ws);
+    k_flag_counts<<<nb, SCAN_TPB, 0, st>>>(flags, n, want, counts);
+    k_flag_compact<<<nb, SCAN_TPB, 0, st>>>(flags, n, want, counts, idx, count);
+    return check_launch("k_flag_compact");
+}
+
+int prl_gather_rows(const float *rows, const int32_t *idx, const int32_t *count, int64_t max_rows, int width, float *out,
+                    void *stream) {
+    PRL_REQUIRE(width > 0 && max_rows >= 0 && count, "prl_gather_rows: bad arguments");
+    if (max_rows == 0) return PRL_OK;
+    const int64_t total = max_rows * width;
+    const int nb = (int)min((int64_t)148 * 8, (total + 255) / 256);
+    k_gather_rows<<<nb, 256, 0, (cudaStream_t)stream>>>(rows, idx, count, width, out);
+    return check_launch("k_gather_rows");
+}
+
+int prl_mask_update(uint8_t *terminal, const int32_t *active_idx, const uint8_t *dones, int n, void *stream) {
+    if (n <= 0) return PRL_OK;
+    PRL_REQUIRE(terminal && active_idx && dones, "prl_mask_update: null pointer");
+    k_mask_update<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(terminal, active_idx, dones, n);
+    return check_launch("k_mask_update");
+}
+
+int prl_buffer_append(int E, int T_cap, int n, const int32_t *active_idx, const float *states, int obs_dim,
+                      const float *actions, int act_width, const float *rewards, const float *dones, float *buf_states,
+                      float *buf_actions, float *buf_rewards, float *buf_dones, int32_t *lengths, int32_t *overflow,
+                      void *stream) {
+    if (n <= 0) return PRL_OK;
+    PRL_REQUIRE(E > 0 && T_cap > 0 && n <= E && obs_dim > 0 && act_width > 0, "prl_buffer_append: bad sizes");
+    k_buffer_append<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(E, T_cap, n, active_idx, states, obs_dim, actions, act_width,
+                                                                rewards, dones, buf_states, buf_actions, buf_rewards,
+                                                                buf_dones, lengths, overflow);
+    return check_launch("k_buffer_append");
+}
+
+int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const float *buf_states, const float *buf_actions,
+                        const float *buf_rewards, const float *buf_dones, int32_t *lengths, int64_t base, int64_t capacity,
+                        float *mem_states, float *mem_actions, float *mem_rewards, float *mem_dones, int64_t *total,
+                        void *ws, size_t ws_bytes, void *stream) {
+    PRL_REQUIRE(E > 0 && T_cap > 0 && total && ws && ws_bytes >= prl_scan_ws_bytes(E), "prl_buffer_transfer: bad arguments / workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = cdiv(E, SCAN_TPB);
+    int32_t *sums = static_cast<int32_t *>(ws);
+    int64_t *offsets = reinterpret_cast<int64_t *>(static_cast<char *>(ws) + (((size_t)(nb + 1) * sizeof(int32_t) + 7) & ~(size_t)7));
+    k_len_block_sums<<<nb, SCAN_TPB, 0, st>>>(lengths, E, sums);
+    k_len_offsets<<<nb, SCAN_TPB, 0, st>>>(lengths, E, sums, base, offsets, total);
+    const int tb = cdiv(E, 128);
+    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, obs_dim, buf_states, lengths, offsets, mem_states, capacity);
+    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, act_width, buf_actions, lengths, offsets, mem_actions, capacity);
+    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_rewards, lengths, offsets, mem_rewards, capacity);
+    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_dones, lengths, offsets, mem_dones, capacity);
+    k_zero_i32<<<cdiv(E, 256), 256, 0, st>>>(lengths, E);
+    return check_launch("k_transfer");
+}
+
+int prl_policy_act(const float *params, int is_continuous, int obs_dim, int action_dim, float action_scaling,
+                   const float *states, const int32_t *row_ids, int64_t n, uint64_t seed, uint64_t call_index,
+                   void *actions, float *dist, void *stream) {
+    PRL_REQUIRE(params && obs_dim > 0 && action_dim > 0 && n >= 0, "prl_policy_act: bad arguments");
+    if (n == 0) return PRL_OK;
+    PRL_REQUIRE(states && actions, "prl_policy_act: null pointer");
+    const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
+    const size_t smem = act_smem_floats(L, TPB) * sizeof(float);
+    PRL_REQUIRE(smem <= 227 * 1024, "prl_policy_act: observ_dim=%d action_dim=%d needs %zu B shared memory (> 227 KB)", obs_dim, action_dim, smem);
+    PRL_CUDA(cudaFuncSetAttribute(k_policy_act, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_policy_act<<<cdiv(n, TPB), TPB, smem, (cudaStream_t)stream>>>(params, L, action_scaling, states, row_ids, n, seed, call_index, actions, dist);
+    return check_launch("k_policy_act");
+}
+
+int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
+                const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
+                float *buf_rewards, float *buf_dones, int32_t *lengths, double *scores, void *stream) {
+    PRL_REQUIRE(E > 0 && T_cap > 0 && state && elapsed && terminal && buf_states && buf_actions && buf_rewards && buf_dones &&
+                    lengths && scores, "prl_rollout: bad arguments");
+    PRL_REQUIRE(tape || params, "prl_rollout: need policy parameters or an action tape");
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        cudaStream_t st = (cudaStream_t)stream;
+        const PolicyLayout L = make_policy_layout(ENV::CONT, ENV::O, ENV::A);
+        if (tape) {
+            k_rollout<ENV, true><<<cdiv(E, TPB), TPB, 0, st>>>(E, T_cap, params, L, action_scaling, seed, episode, tape, state, elapsed,
+                                                              terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores);
+        } else {
+            const size_t smem = act_smem_floats(L, TPB) * sizeof(float);
+            PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_rollout<ENV, false><<<cdiv(E, TPB), TPB, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
+                                                                 elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
+                                                                 lengths, scores);
+        }
+        return check_launch("k_rollout");
+    });
+}
+
+}  // extern "C"

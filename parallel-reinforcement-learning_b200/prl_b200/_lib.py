@@ -1,0 +1,94 @@
+"""ctypes binding of libprl_b200.so (the C ABI declared in include/prl_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call returns a non-zero status, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprl_b200.so")
+
+ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2}
+ACT_I32, ACT_I64, ACT_F32 = 0, 1, 2
+
+_vp, _i32, _i64, _u64, _u32, _f32, _f64, _sz = (C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float,
+                                                C.c_double, C.c_size_t)
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol include/prl_b200.h declares
+PROTOTYPES = {
+    "prl_last_error": (C.c_char_p, []),
+    "prl_version": (_i32, []),
+    "prl_env_info": (_i32, [_i32, _ip, _ip, _ip, _ip, _ip]),
+    "prl_policy_param_count": (_i64, [_i32, _i32, _i32]),
+    "prl_rnd_param_count": (_i64, [_i32, _i32]),
+    "prl_scan_ws_bytes": (_sz, [_i64]),
+    "prl_test_sincos": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "prl_test_pow2": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "prl_test_philox": (_i32, [_u64, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "prl_env_reset": (_i32, [_i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "prl_env_set_state": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_env_get_state": (_i32, [_i32, _i32, _vp, _vp, _vp]),
+    "prl_env_step": (_i32, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "prl_compact_indices": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "prl_gather_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "prl_mask_update": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "prl_buffer_append": (_i32, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_buffer_transfer": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _sz, _vp]),
+    "prl_policy_act": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp]),
+    "prl_policy_evaluate": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "prl_rollout": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_gae": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp, _sz, _vp]),
+    "prl_gae_ws_bytes": (_sz, [_i64]),
+    "prl_gae_columns": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _vp, _vp]),
+    "prl_adv_normalize": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "prl_update_ws_floats": (_sz, [_i32, _i32, _i32, _i64]),
+    "prl_ppo_grad": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "prl_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _vp, _vp]),
+    "prl_rnd_intrinsic": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f32, _vp, _vp, _vp]),
+    "prl_rnd_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class PrlError(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None):
+    """dlopen the in-tree shared library and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise PrlError(f"{path} is missing - run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Invoke a status-returning entry point; raise PrlError with prl_last_error() on failure."""
+    lib = load_library()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise PrlError(f"{name} failed ({rc}): {lib.prl_last_error().decode()}")
+
+
+def fn(name: str):
+    return getattr(load_library(), name)
+
+
+def env_info(env_id: str):
+    v = [C.c_int() for _ in range(5)]
+    call("prl_env_info", ENV_IDS[env_id], *[C.byref(x) for x in v])
+    S, O, A, cont, ms = [x.value for x in v]
+    return dict(S=S, O=O, A=A, continuous=bool(cont), max_steps=ms, code=ENV_IDS[env_id])

@@ -1,0 +1,310 @@
+"""GPU parity tests, kernel level: every CUDA entry point against the oracle (oracle/) and against the golden
+fixtures produced by the real reference.  All calls go through the C ABI (prl_b200.ops -> ctypes -> libprl_b200.so).
+
+Tolerances: bit-exact for everything integer / fp64-physics / float32-GAE; 1e-5 relative (stated per test) for the
+float32 network math, as BASELINE.json's north_star specifies."""
+import numpy as np
+import pytest
+import torch as t
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cref, ppo as oppo  # noqa: E402
+
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1"}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not t.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from prl_b200 import ops as _ops
+
+    return _ops
+
+
+def dev(a):
+    return t.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize])
+
+
+def philox_np(seed, c0, c1, c2, c3):
+    """Philox4x32-10 on the host (test-side restatement of csrc/common.cuh::Philox)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return np.array([c0, c1, c2, c3], np.uint32)
+
+
+# ------------------------------------------------------------------------------------------------ elementary functions
+def test_device_sincos_equals_libm(ops):
+    rng = np.random.default_rng(0)
+    parts = [rng.uniform(lo, hi, 400_000) for lo, hi in
+             [(-1e-7, 1e-7), (-0.21, 0.21), (-0.8555, 0.8555), (0.85, 2.43), (-2.43, -0.85), (-8, 8), (-90, 90), (-1e5, 1e5)]]
+    x = np.concatenate(parts + [np.array([0.0, -0.0, 0.126, 0.855469, 2.426265, np.pi / 2, np.pi, 1.0, -1.0])])
+    s, c = ops.test_sincos(dev(x))
+    assert np.array_equal(bits(s.cpu().numpy()), bits(np.sin(x)))
+    assert np.array_equal(bits(c.cpu().numpy()), bits(np.cos(x)))
+
+
+def test_philox_matches_host_restatement(ops):
+    for seed, c in [(0, (0, 0, 0, 0)), (0x123456789ABCDEF, (7, 11, 13, 17)), (2**64 - 1, (2**32 - 1, 5, 2**31, 9))]:
+        assert np.array_equal(ops.test_philox(seed, *c), philox_np(seed, *c))
+
+
+# ------------------------------------------------------------------------------------------------ rollout (teacher forced)
+def run_taped_rollout(ops, env_id, init_state, tape, T):
+    E = init_state.shape[0]
+    info_env = ops.EnvState(env_id, E, T)
+    info = info_env.info
+    aw = info["A"] if info["continuous"] else 1
+    info_env.set_state(dev(init_state))
+    buf = ops.RolloutBuffer(E, T, info["O"], aw)
+    scores = t.zeros(2, dtype=t.float64, device="cuda")
+    tp = dev(tape.astype(np.float32 if info["continuous"] else np.int32))
+    ops.rollout(info_env, buf, None, 1.0, 0, 0, scores, tape=tp)
+    cap = E * T
+    ms = t.empty(cap, info["O"], device="cuda"); ma = t.empty(cap, aw, device="cuda")
+    mr = t.empty(cap, device="cuda"); md = t.empty(cap, device="cuda")
+    total = t.zeros(1, dtype=t.int64, device="cuda")
+    lengths = buf.lengths.clone()
+    buf.transfer(ms, ma, mr, md, 0, total)
+    N = int(total.item())
+    assert int(buf.lengths.sum().item()) == 0  # buffer.clear()
+    return dict(N=N, states=ms[:N].cpu().numpy(), actions=ma[:N].cpu().numpy(), rewards=mr[:N].cpu().numpy(),
+                dones=md[:N].cpu().numpy(), lengths=lengths.cpu().numpy(), final_state=info_env.get_state().cpu().numpy(),
+                scores=scores.cpu().numpy(), terminal=info_env.terminal.cpu().numpy())
+
+
+@pytest.mark.parametrize("key", list(ENVS))
+def test_fused_rollout_matches_reference_worker_golden(ops, golden, key):
+    """Device worker() vs the REAL reference's AsyncPPO.worker (tests/golden): flat env-major buffer bit-exact."""
+    g = golden("rollout_" + key)
+    E, T = int(g["E"]), int(g["T"])
+    tape = np.zeros((T,) + g["tape"].shape[1:], g["tape"].dtype)
+    tape[: len(g["tape"])] = g["tape"]
+    r = run_taped_rollout(ops, ENVS[key], g["init_state"], tape, T)
+    assert r["N"] == len(g["states"]) == int(g["step_score"]) == int(r["scores"][1])
+    assert np.array_equal(bits(r["states"]), bits(g["states"]))
+    assert np.array_equal(bits(r["actions"].reshape(g["actions"].shape)), bits(g["actions"]))
+    assert np.array_equal(bits(r["rewards"]), bits(g["rewards"]))
+    assert np.array_equal(bits(r["dones"]), bits(g["dones"]))
+    assert np.array_equal(bits(r["final_state"]), bits(g["final_state"]))
+    assert r["terminal"].all()
+    assert r["scores"][0] == pytest.approx(float(g["reward_score"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("key,E,T", [("cartpole", 4096, 128), ("pendulum", 2048, 200), ("acrobot", 1024, 120)])
+def test_fused_rollout_matches_c_oracle(ops, key, E, T):
+    env_id = ENVS[key]
+    rng = np.random.default_rng(42)
+    d = cref.env_dims(env_id)
+    if key == "cartpole":
+        s0 = rng.uniform(-0.05, 0.05, (E, 4)); tape = rng.integers(0, 2, (T, E)).astype(np.int32)
+    elif key == "pendulum":
+        s0 = rng.uniform([-np.pi, -1], [np.pi, 1], (E, 2)); tape = (2 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
+    else:
+        s0 = rng.uniform(-0.1, 0.1, (E, 4)).astype(np.float32).astype(np.float64); tape = rng.integers(0, 3, (T, E)).astype(np.int32)
+    want = cref.rollout(env_id, s0, tape, T)
+    got = run_taped_rollout(ops, env_id, s0, tape, T)
+    assert got["N"] == want["N"]
+    assert np.array_equal(got["lengths"], want["lengths"])
+    for k in ("states", "rewards", "dones", "final_state"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), k
+    assert np.array_equal(bits(got["actions"].reshape(want["actions"].shape)), bits(want["actions"]))
+
+
+# ------------------------------------------------------------------------------------------------ utils kernels
+def test_compaction_and_mask_update(ops):
+    rng = np.random.default_rng(1)
+    for n in (1, 31, 1024, 1025, 70_001):
+        mask = rng.random(n) < 0.37
+        idx, cnt = ops.compact_indices(dev(mask.astype(np.uint8)), want=False)
+        c = int(cnt.item())
+        want = np.arange(n)[~mask]
+        assert c == len(want) and np.array_equal(idx[:c].cpu().numpy(), want)
+        dones = rng.random(c) < 0.5
+        term = dev(mask.astype(np.uint8))
+        ops.mask_update(term, idx, dev(dones.astype(np.uint8)), c)
+        m2 = mask.copy(); m2[np.where(~m2)[0]] = dones
+        assert np.array_equal(term.cpu().numpy().astype(bool), m2)
+        rows = rng.standard_normal((c, 5)).astype(np.float32)
+        if c:
+            keep, kc = ops.compact_indices(dev(dones.astype(np.uint8)), want=False)
+            out = ops.gather_rows(dev(rows), keep, kc, c)
+            k = int(kc.item())
+            assert np.array_equal(out[:k].cpu().numpy(), rows[~dones])
+
+
+def test_buffer_append_transfer_matches_reference_utils(ops, golden):
+    g = golden("utils")
+    E = len(g["mask"])
+    buf = ops.RolloutBuffer(E, 8, 3, 1)
+    for i in range(int(g["ba_nsteps"])):
+        m = g[f"ba_m{i}"]
+        idx, cnt = ops.compact_indices(dev(m.astype(np.uint8)), want=False)
+        n = int(cnt.item())
+        buf.append(idx, n, dev(g[f"ba_s{i}"].astype(np.float32)), dev(g[f"ba_a{i}"].astype(np.float32).reshape(n, 1)),
+                   dev(g[f"ba_r{i}"].astype(np.float32)), dev(g[f"ba_d{i}"].astype(np.float32)))
+    cap = len(g["ba_rewards"]) + 4
+    ms = t.empty(cap, 3, device="cuda"); ma = t.empty(cap, 1, device="cuda"); mr = t.empty(cap, device="cuda"); md = t.empty(cap, device="cuda")
+    total = t.zeros(1, dtype=t.int64, device="cuda")
+    buf.transfer(ms, ma, mr, md, 0, total)
+    N = int(total.item())
+    assert N == len(g["ba_rewards"])
+    assert np.array_equal(ms[:N].cpu().numpy(), g["ba_states"]) and np.array_equal(ma[:N, 0].cpu().numpy(), g["ba_actions"])
+    assert np.array_equal(mr[:N].cpu().numpy(), g["ba_rewards"]) and np.array_equal(md[:N].cpu().numpy(), g["ba_dones"])
+    assert int(buf.overflow.item()) == 0
+
+
+# ------------------------------------------------------------------------------------------------ GAE
+@pytest.mark.parametrize("name", ["discrete", "continuous", "rnd"])
+def test_gae_flat_matches_reference_golden(ops, golden, name):
+    g = golden("learn_" + name)
+    nv = dev(np.array([g["gae_next_value"]], np.float32))
+    out = ops.gae(dev(g["gae_rewards"]), dev(g["gae_dones"]), dev(g["gae_values"]), float(g["gamma"]), float(g["GAE_lambda"]), next_value=nv)
+    assert np.array_equal(bits(out.cpu().numpy()), bits(g["gae_returns"]))
+    adv, _ = ops.adv_normalize(out, dev(g["gae_values"]))
+    np.testing.assert_allclose(adv.cpu().numpy(), g["advantages"], rtol=1e-5, atol=1e-6)
+
+
+def test_gae_flat_random_segments_bit_exact(ops):
+    rng = np.random.default_rng(2)
+    for N, p_done in [(1, 0.5), (257, 0.0), (100_003, 0.02), (300_000, 0.2)]:
+        r = rng.standard_normal(N).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
+        d = (rng.random(N) < p_done).astype(np.float32)
+        want = cref.gae(r, d, v, v[-1], 0.995, 0.95)
+        got = ops.gae(dev(r), dev(d), dev(v), 0.995, 0.95)
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), (N, p_done)
+
+
+def test_gae_columns_bit_exact_and_equal_to_flat(ops):
+    rng = np.random.default_rng(3)
+    T, E = 64, 5000
+    lens = rng.integers(1, T + 1, E).astype(np.int32)
+    r = rng.standard_normal((T, E)).astype(np.float32); v = rng.standard_normal((T, E)).astype(np.float32)
+    d = np.zeros((T, E), np.float32)
+    d[lens - 1, np.arange(E)] = 1.0
+    got = ops.gae_columns(dev(r), dev(d), dev(v), dev(lens), 0.995, 0.95).cpu().numpy()
+    for e in range(0, E, 97):
+        L = lens[e]
+        want = cref.gae(r[:L, e], d[:L, e], v[:L, e], v[L - 1, e], 0.995, 0.95)
+        assert np.array_equal(bits(got[:L, e]), bits(want))
+
+
+def test_adv_normalize_matches_oracle(ops):
+    rng = np.random.default_rng(4)
+    for N in (5, 1000, 1_000_003):
+        ret = (rng.standard_normal(N) * 3 + 1).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
+        want, mean, sd = cref.adv_norm(ret, v)
+        got, stats = ops.adv_normalize(dev(ret), dev(v))
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+        s = stats.cpu().numpy()
+        assert s[2] == N and s[0] / N == pytest.approx(mean, rel=1e-9, abs=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ networks
+LEARN = [("discrete", "cartpole"), ("continuous", "pendulum"), ("rnd", "acrobot")]
+
+
+@pytest.mark.parametrize("name,roll", LEARN)
+def test_policy_evaluate_and_dist_match_reference(ops, golden, name, roll):
+    g, r = golden("learn_" + name), golden("rollout_" + roll)
+    cont, O, A = bool(g["is_continuous"]), int(g["O"]), int(g["A"])
+    params = dev(g["init_flat"])
+    s = dev(r["states"]); a = dev(r["actions"].reshape(len(r["states"]), -1))
+    logp, val, ent = ops.policy_evaluate(params, cont, O, A, s, a)
+    np.testing.assert_allclose(logp.cpu().numpy(), g["eval_logp"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(val.cpu().numpy(), g["eval_value"], rtol=1e-5, atol=1e-5)
+    assert float(ent.item()) / len(r["states"]) == pytest.approx(float(g["eval_entropy"]), rel=1e-5)
+    act, dist = ops.policy_act(params, cont, O, A, 2.0, s, seed=5, call_index=0, want_dist=True)
+    if cont:
+        np.testing.assert_allclose(dist[:, :A].cpu().numpy(), g["dist_mu"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(dist[:, A:].cpu().numpy(), g["dist_std"], rtol=1e-5, atol=1e-6)
+        assert act.dtype == t.float32 and tuple(act.shape) == (len(r["states"]), A) and float(act.abs().max()) <= 2.0
+    else:
+        np.testing.assert_allclose(dist.cpu().numpy(), g["dist_probs"], rtol=1e-5, atol=1e-6)
+        assert act.dtype == t.int64 and int(act.min()) >= 0 and int(act.max()) < A
+
+
+def test_categorical_sampler_is_inverse_cdf_of_philox(ops, golden):
+    """Sampling cannot be bit-compared with torch.multinomial: check that the device action is the
+    inverse CDF of the device-reported probabilities under the host-recomputed Philox uniform, and the frequencies."""
+    g = golden("learn_discrete")
+    params = dev(g["init_flat"])
+    n = 20000
+    s = t.randn(n, 4, device="cuda")
+    act, dist = ops.policy_act(params, False, 4, 2, 1.0, s, seed=99, call_index=(3 << 32) | 7, want_dist=True)
+    act, p = act.cpu().numpy(), dist.cpu().numpy()
+    for row in range(0, n, 997):
+        u32 = philox_np(99, row, 7, (2 << 24) | 0, 3)[0]
+        u = (np.float32(u32 >> 8) + np.float32(0.5)) * np.float32(1 / 16777216)
+        cum = np.cumsum(p[row].astype(np.float32))
+        want = int(np.argmax(u < cum)) if (u < cum).any() else 1
+        assert act[row] == want
+    freq = act.mean()
+    assert abs(freq - p[:, 1].mean()) < 4 * np.sqrt(0.25 / n)
+
+
+@pytest.mark.parametrize("name,roll", [("discrete_1step", "cartpole"), ("continuous_1step", "pendulum")])
+def test_ppo_grad_and_adamw_match_reference_single_step(ops, golden, name, roll):
+    """One optimiser step on one minibatch: gradient vs oracle autograd, post-update weights vs the REAL reference."""
+    g, r = golden("learn_" + name), golden("rollout_" + roll)
+    cont, O, A = bool(g["is_continuous"]), int(g["O"]), int(g["A"])
+    N = len(r["states"])
+    params = dev(g["init_flat"]).clone()
+    s = dev(r["states"]); a = dev(r["actions"].reshape(N, -1))
+    logp, val, _ = ops.policy_evaluate(params, cont, O, A, s, a)
+    ret = dev(g["gae_returns"]); adv = dev(g["advantages"])
+    grad = t.zeros_like(params); loss = t.zeros(4, dtype=t.float64, device="cuda")
+    ws = t.empty(ops.update_ws_floats(cont, O, A, N), device="cuda")
+    ops.ppo_grad(params, cont, O, A, s, a, logp, adv, ret, float(g["policy_clip"]), 1.0 / N, grad, loss, ws)
+    # oracle gradient (torch autograd on the CPU restatement)
+    p = oppo.unflatten(g["init_flat"], cont, O, A)
+    keys = oppo.param_keys(cont)
+    for k in keys:
+        p[k].requires_grad_(True)
+    old_lp = t.from_numpy(g["eval_logp"])
+    lo = oppo.ppo_loss(p, cont, t.from_numpy(r["states"]), t.from_numpy(r["actions"]), old_lp, t.from_numpy(g["advantages"]),
+                       t.from_numpy(g["gae_returns"]), float(g["policy_clip"]))
+    want = t.cat([x.reshape(-1) for x in t.autograd.grad(lo, [p[k] for k in keys])]).numpy()
+    got = grad.cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-5 * scale + 1e-7, (np.abs(got - want).max(), scale)
+    l = loss.cpu().numpy()
+    total = l[0] / N + 0.5 * l[1] / N - 0.01 * l[2] / N
+    assert total == pytest.approx(float(lo), rel=1e-5)
+    m = t.zeros_like(params); v = t.zeros_like(params)
+    ops.adamw_step(params, grad, m, v, 1, float(g["lr"]))
+    np.testing.assert_allclose(params.cpu().numpy(), g["post_flat"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.cpu().numpy(), g["post_exp_avg"], rtol=1e-4, atol=1e-8)
+
+
+def test_rnd_intrinsic_and_grad_match_reference(ops, golden):
+    g, r = golden("learn_rnd"), golden("rollout_acrobot")
+    O = int(g["O"])
+    tflat = np.concatenate([g[f"rnd_init.target_net.{k}"].ravel() for k in oppo.RND_KEYS])
+    pflat = np.concatenate([g[f"rnd_init.pred_net.{k}"].ravel() for k in oppo.RND_KEYS])
+    s = dev(r["states"])
+    out = ops.rnd_intrinsic(dev(tflat), dev(pflat), O, O, s, 0.001)
+    np.testing.assert_allclose(out.cpu().numpy(), g["rnd_intrinsic"], rtol=1e-5, atol=1e-9)
+    # one update_pred pass in chunks of mini_batch_size, AdamW lr 1e-3, no clipping (RND.py:96-115)
+    mb = int(g["mini_batch_size"])
+    pp = dev(pflat).clone(); tp = dev(tflat)
+    m = t.zeros_like(pp); v = t.zeros_like(pp); grad = t.zeros_like(pp)
+    loss = t.zeros(4, dtype=t.float64, device="cuda")
+    ws = t.empty(ops.update_ws_floats(False, O, O, mb) + 4096, device="cuda")
+    step = 0
+    for i in range(0, len(r["states"]), mb):
+        step += 1
+        ops.rnd_grad(tp, pp, O, O, s[i:i + mb].contiguous(), grad, loss, ws)
+        ops.adamw_step(pp, grad, m, v, step, 1e-3, max_norm=0.0)
+    want = np.concatenate([g[f"rnd_post.pred_net.{k}"].ravel() for k in oppo.RND_KEYS])
+    np.testing.assert_allclose(pp.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
