@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py - the reference's headline metric on B200: env-steps/s end to end (rollout + GAE + PPO update).
+
+Workload (BASELINE.json configs[1]): CartPole-v1 discrete, num_envs = 65 536 per GPU, one episode per env with
+TimeLimit T = 128 ("synthetic rollout T=128"), then PPO.learn() with k_epochs = 11 and mini_batch_size = 65 536
+(SURVEY.md section 8d).  A "step" = one AsyncPPO.worker() + one PPO.learn(): reset, fused rollout kernel, env-major
+transfer, old-policy evaluation, float32 GAE, advantage normalisation, 11 x ceil(N / 65 536) optimiser steps.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          the B200 arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                          the CPU arm: the oracle port of the reference's
+                                                                Python path on the host cores, bounded sample
+
+One JSON line on stdout (rank 0).  `value`: device-resident (random resets drawn on the GPU); `e2e`: the same steps
+through the public API with the start states coming from pinned host memory every step and the updated weights +
+scores read back every step.  `roofline`: the dominant kernel, timed live with CUDA events on the launching stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "parallel-reinforcement-learning_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "env_steps_per_sec_end_to_end_rollout_gae_update"
+UNIT = "env-steps/s"
+# algorithmic FLOPs of one sample-epoch of the update, CartPole shapes: forward 2*(O*64 + 2*64^2 + 64*A
+# + 64) = 17 280, forward + backward ~ 3x
+FLOPS_PER_SAMPLE_EPOCH = 51_840.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--horizon", type=int, default=128)
+    ap.add_argument("--k-epochs", type=int, default=11)
+    ap.add_argument("--mini-batch", type=int, default=65536, help="minibatch rows per GPU")
+    ap.add_argument("--cpu-sample-envs", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_steps(envs: int, horizon: int, k_epochs: int, mini_batch: int, n_steps: int, warmup: int, threads: int):
+    """The reference's CPU path restated (oracle/): per-env Python env objects stepped in a loop, list-of-lists
+    VecMemory, torch-CPU ActorCritic for get_action, then learn() = torch-CPU float32 autograd + AdamW.  Returns
+    (env steps, seconds) over the timed steps.  This is the checker code being TIMED as the baseline, nothing more."""
+    import numpy as np
+    import torch as t
+
+    from oracle import envs as oenvs
+    from oracle import ppo as oppo
+    from oracle import vec as ovec
+
+    t.set_num_threads(threads)
+    t.manual_seed(0)
+    np.random.seed(0)
+    cont, O, A = False, 4, 2
+    shapes = oppo.param_shapes(cont, O, A)
+    params = {}
+    for k in oppo.param_keys(cont):  # reference init (ActorCritic.py:66-80)
+        w = t.empty(shapes[k])
+        if k.endswith("0.weight") or k.endswith("3.weight"):
+            t.nn.init.xavier_uniform_(w)
+        elif k.endswith("3.bias"):
+            t.nn.init.normal_(w, 0, 0.01)
+        elif k.endswith("1.weight"):
+            w.fill_(1.0)
+        else:
+            w.zero_()
+        params[k] = w
+    vec = ovec.Vectorizer(oenvs.make("CartPole-v1", max_episode_steps=horizon), envs)
+    opt = oppo.AdamW([params[k] for k in oppo.param_keys(cont)], lr=1e-3)
+
+    def act(states):
+        with t.no_grad():
+            _, (probs,) = oppo.dist_params(params, cont, t.from_numpy(states))
+            return t.multinomial(probs, 1).squeeze(-1).numpy()
+
+    total_steps, total_s = 0, 0.0
+    for it in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        mem = ovec.FlatMemory()
+        _, ss = ovec.worker(vec, ovec.PerEnvMemory(envs), act, mem)
+        m = dict(states=np.array(mem.states, np.float32), actions=np.array(mem.actions, np.float32),
+                 rewards=np.array(mem.rewards, np.float32), dones=np.array(mem.dones, np.float32))
+        oppo.learn(params, cont, m, lr=1e-3, k_epochs=k_epochs, policy_clip=0.2, gae_lambda=0.95, gamma=0.995,
+                   mini_batch_size=mini_batch, opt=opt)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            total_steps += ss
+            total_s += dt
+    return total_steps, total_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, secs = cpu_port_steps(args.cpu_sample_envs, args.horizon, args.k_epochs, args.mini_batch, args.steps, args.warmup, threads)
+    v = steps / secs
+    sample = f"{args.cpu_sample_envs} of {args.envs} envs per step, same T={args.horizon}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 networks / f64 physics", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": f"CartPole-v1 discrete, num_envs={args.envs}/GPU, one episode per env with TimeLimit T={args.horizon}, "
+                        f"PPO.learn k_epochs={args.k_epochs}, mini_batch_size={args.mini_batch}/GPU, batch_size=1024, lr=1e-3",
+            "num_envs_per_gpu": args.envs, "horizon": args.horizon, "k_epochs": args.k_epochs, "mini_batch_per_gpu": args.mini_batch,
+            "parallelism": f"env-sharded dp{world}",
+            "l2": "256 MiB buffer rewritten between steps inside the timed region (L2 flush); the [T][C][E] rollout buffer alone is 235 MB > 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 <= ts <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch as t
+
+    import prl_b200
+    from AsyncTools.AsyncPPO import AsyncPPO
+    from PPO import PPO
+    from prl_b200 import _lib
+    from prl_b200 import dist as pdist
+
+    comm = pdist.init_from_env()
+    rank = comm.rank if comm else 0
+    world = comm.world_size if comm else 1
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 under torch.distributed.run")
+    dev = t.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    t.cuda.set_device(dev)
+
+    E, T = args.envs, args.horizon
+    t.manual_seed(0)  # identical initial weights and sampling seed on every rank
+    ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=1e-3, k_epochs=args.k_epochs, batch_size=1024,
+              mini_batch_size=args.mini_batch * world)
+    ppo.show_progress = False
+    ppo._seed += rank  # different action noise per shard
+    t.manual_seed(1234 + rank)  # different env reset stream per shard
+    ap = AsyncPPO(env=prl_b200.make("CartPole-v1", max_episode_steps=T), ppo=ppo, num_envs=E, steps=1)
+    flush = t.empty(256 << 20, dtype=t.uint8, device=dev)
+    rng = np.random.default_rng(1234 + rank)
+    host_states = t.from_numpy(rng.uniform(-0.05, 0.05, (E, 4))).pin_memory()       # e2e: start states from the host
+    host_weights = t.empty(ppo.policy.flat.numel(), dtype=t.float32).pin_memory()   # e2e: results read back
+    host_scores = t.empty(2, dtype=t.float64).pin_memory()
+
+    def step(e2e: bool):
+        ap.step_score = 0
+        ap.reward_score = 0
+        ap.worker(initial_states=host_states if e2e else None)
+        n = int(ap.step_score)
+        ppo.learn()
+        if e2e:
+            host_weights.copy_(ppo.policy.flat, non_blocking=True)
+            host_scores.copy_(ap._scores, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+        flush.fill_(1)
+        return n
+
+    def timed(e2e: bool, k: int, profile: bool):
+        if comm:
+            comm.barrier()
+        t.cuda.synchronize()
+        counts0 = dict(_lib.CALL_COUNTS)
+        if profile:
+            _lib.profile_calls(True)
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        n = sum(step(e2e) for _ in range(k))
+        e1.record()
+        t.cuda.synchronize()
+        w1 = time.time()
+        prof = _lib.profile_calls(False) if profile else None
+        ms = t.tensor([e0.elapsed_time(e1)], dtype=t.float64, device=dev)
+        tot = t.tensor([float(n)], dtype=t.float64, device=dev)
+        if comm:
+            comm.allreduce_max_(ms)
+            comm.allreduce_(tot)
+            comm.barrier()
+        counts = {k_: v - counts0.get(k_, 0) for k_, v in _lib.CALL_COUNTS.items() if v - counts0.get(k_, 0)}
+        return float(tot.item()), float(ms.item()), counts, prof, (w0, w1)
+
+    for _ in range(args.warmup):
+        step(False)
+    step(True)  # touch the e2e path once
+    clocks = ClockSampler(dev.index) if rank == 0 else None
+    time.sleep(0.3)
+    n_dev, ms_dev, counts, prof, (w0, w1) = timed(False, args.steps, profile=True)
+    clk = clocks.summary(w0, w1) if clocks else None
+    n_e2e, ms_e2e, _, _, _ = timed(True, args.steps, profile=False)
+
+    # per-entry-point device time (CUDA events on the launching stream, this rank)
+    per = {}
+    for name, evs in prof.items():
+        per[name] = {"calls": len(evs), "ms": sum(a.elapsed_time(b) for a, b in evs)}
+    pk = peaks()
+    roof = None
+    if "prl_ppo_grad" in per:
+        g = per["prl_ppo_grad"]
+        rows_epochs = n_dev / world * args.k_epochs            # sample-epochs this rank pushed through the update kernel
+        tf = rows_epochs * FLOPS_PER_SAMPLE_EPOCH / (g["ms"] * 1e-3) / 1e12
+        roof = {"kernel": "k_ppo_grad (prl_ppo_grad: fused forward + loss + backward, fp32 FMA path)", "bound": "tensor", "achieved": tf,
+                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
+                "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
+                "share_of_step": g["ms"] / ms_dev}
+    hbm = {}
+    bytes_per = {"prl_rollout": 102.0, "prl_gae": 16.0, "prl_adv_normalize": 10.0, "prl_buffer_transfer": 56.0 + 4.0 * E * args.steps / max(n_dev / world, 1)}
+    for name, b in bytes_per.items():
+        if name in per and per[name]["ms"] > 0:
+            gbs = (n_dev / world) * b / (per[name]["ms"] * 1e-3) / 1e9
+            hbm[name] = {"GB/s": gbs, "frac_of_" + pk["source"] + "_hbm": gbs / pk["hbm"], "bytes_per_transition": b, "ms": per[name]["ms"], "calls": per[name]["calls"]}
+
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": n_dev / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 networks / f64 physics", "data": "synthetic",
+        "config": workload_config(args, world),
+        "env_steps_per_step": n_dev / args.steps,
+        "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_states.numel() * 8),
+                "d2h_bytes_per_step": int(host_weights.numel() * 4 + 16 + 16), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": _lib.launches(counts),
+        "calls": counts,
+        "clocks": clk,
+        "roofline": roof,
+        "hbm_kernels": hbm,
+        "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cs, csec = cpu_port_steps(args.cpu_sample_envs, T, args.k_epochs, args.mini_batch, 1, 0, threads)
+        out["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"1 step of {args.cpu_sample_envs} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
+                                         f"{cs} env-steps in {csec:.1f} s"}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -253,3 +253,12 @@ void orc_adv_norm(const float *returns, const float *values, int64_t N, float *a
     if (mean_out) *mean_out = mean;
     if (std_out) *std_out = sd;
 }
+
+/* libm pass-throughs: what numpy's float64 / float32 SCALAR `x ** 2` evaluates (npy_pow / npy_powf).  The exponent is
+ * passed at run time and the file is built with -fno-builtin so the call cannot be folded into x*x. */
+void orc_pow_scalar(const double *x, double y, double *out, const float *xf, float yf, float *outf, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (x) out[i] = pow(x[i], y);
+        if (xf) outf[i] = powf(xf[i], yf);
+    }
+}

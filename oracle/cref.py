@@ -107,3 +107,15 @@ def adv_norm(returns, values):
     m, s = C.c_double(), C.c_double()
     lib().orc_adv_norm(_p(r), _p(v), C.c_int64(r.size), _p(out), C.byref(m), C.byref(s))
     return out, m.value, s.value
+
+
+def pow2(x64=None, x32=None):
+    """libm pow(x, 2.0) / powf(x, 2.0f) elementwise - numpy's float64 / float32 scalar `x ** 2`."""
+    n = len(x64) if x64 is not None else len(x32)
+    o64 = np.empty(n, np.float64) if x64 is not None else None
+    o32 = np.empty(n, np.float32) if x32 is not None else None
+    lib().orc_pow_scalar(_p(np.ascontiguousarray(x64, np.float64)) if x64 is not None else None, C.c_double(2.0),
+                         _p(o64) if o64 is not None else None,
+                         _p(np.ascontiguousarray(x32, np.float32)) if x32 is not None else None, C.c_float(2.0),
+                         _p(o32) if o32 is not None else None, C.c_int64(n))
+    return o64, o32

@@ -101,6 +101,7 @@ class Memory:
         """Make room for `capacity` rows in HBM, keeping what is already there."""
         if self._dev and self._dev_cap >= capacity and self._dev["states"].shape[1] == obs_dim:
             return
+        capacity = max(int(capacity), 1)
         new = {"states": torch.empty(capacity, obs_dim, dtype=torch.float32, device=device),
                "actions": torch.empty(capacity, act_width, dtype=torch.float32, device=device),
                "rewards": torch.empty(capacity, dtype=torch.float32, device=device),
@@ -112,20 +113,38 @@ class Memory:
         if self._total is None:
             self._total = torch.zeros(1, dtype=torch.int64, device=device)
 
+    def _upload_host(self, obs_dim, act_width, device):
+        """Move items pushed on the host (Memory.push / list +=) into the device rows, in order."""
+        nh = len(self._fields["states"]._host)
+        if not nh:
+            return
+        if self._dev_count:
+            raise RuntimeError("host items and device rows cannot be combined")
+        host = {k: np.array(self._fields[k]._host, dtype=np.float32) for k in FIELDS}
+        a = host["actions"].reshape(nh, -1)
+        self._scalar_actions = host["actions"].ndim == 1
+        self.reserve(nh, obs_dim, act_width, device)
+        self._dev["states"][:nh] = torch.from_numpy(host["states"].reshape(nh, obs_dim)).to(device)
+        self._dev["actions"][:nh] = torch.from_numpy(np.ascontiguousarray(a[:, :act_width])).to(device)
+        self._dev["rewards"][:nh] = torch.from_numpy(host["rewards"].reshape(nh)).to(device)
+        self._dev["dones"][:nh] = torch.from_numpy(host["dones"].reshape(nh)).to(device)
+        for f in self._fields.values():
+            f._host.clear()
+        self._dev_count = nh
+
     def device_view(self, obs_dim, act_width, device):
         """(states [N][O], actions [N][AW], rewards [N], dones [N]) on the device, host items uploaded first."""
-        nh = len(self._fields["states"]._host)
-        if nh:
-            host = {k: np.array(self._fields[k]._host, dtype=np.float32) for k in FIELDS}
-            N = nh + self._dev_count
-            if self._dev_count:
-                raise RuntimeError("host items and device rows cannot be combined")
-            s = torch.from_numpy(host["states"].reshape(N, obs_dim)).to(device)
-            a = torch.from_numpy(host["actions"].reshape(N, -1)).to(device)
-            if a.shape[1] != act_width:
-                a = a[:, :act_width].contiguous()
-            r = torch.from_numpy(host["rewards"].reshape(N)).to(device)
-            d = torch.from_numpy(host["dones"].reshape(N)).to(device)
-            return s, a, r, d
+        self._upload_host(obs_dim, act_width, device)
         n = self._dev_count
         return tuple(self._dev[k][:n] for k in FIELDS)
+
+    def append_from_rollout(self, buf, n_new, scalar_actions=True):
+        """utils.buffer_to_target_buffer_transfer (utils.py:45-50) on the device: the per-env episodes of the rollout
+        buffer are concatenated env-major, time-minor behind the rows already stored; the buffer is cleared."""
+        device = buf.lengths.device
+        self._upload_host(buf.O, buf.AW, device)
+        base = self._dev_count
+        self.reserve(base + int(n_new), buf.O, buf.AW, device)
+        self._scalar_actions = scalar_actions
+        buf.transfer(self._dev["states"], self._dev["actions"], self._dev["rewards"], self._dev["dones"], base, self._total)
+        self._dev_count = base + int(n_new)

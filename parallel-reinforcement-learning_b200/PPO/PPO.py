@@ -1,0 +1,204 @@
+"""Drop-in `PPO` (reference: /root/reference/PPO/PPO.py:13-283) on the sm_100a kernels of libprl_b200.so.
+
+Same constructor arguments, attributes and methods as the reference.  What changes is where the work happens:
+
+  get_action   one fused launch: trunk + policy head + Categorical / tanh-Gaussian sampling (prl_policy_act)
+  learn        stays on the device end to end: old-policy evaluation (1 launch over all N rows), RND reward mixing and
+               predictor updates, float32 GAE in the reference's operation order (prl_gae), advantage normalisation
+               (prl_adv_normalize), then k_epochs x ceil(N / mini_batch_size) strictly sequential steps of
+               [fused forward+loss+backward -> flat gradient (prl_ppo_grad)] -> [NCCL allreduce when sharded] ->
+               [clip_grad_norm_(2.0) + AdamW in one kernel (prl_adamw_step)], no host sync inside the loop.
+
+There is no CPU fallback: constructing a PPO without the shared library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as t
+from torch import nn
+from tqdm import tqdm
+
+from prl_b200 import dist as pdist
+from prl_b200 import ops
+from prl_b200._lib import require_cuda
+from prl_b200.optim import FusedAdamW
+
+from .ActorCritic import ActorCritic
+from .Memory import Memory
+from .RND import RND
+
+
+class PPO:
+    def __init__(
+            self,
+            is_continuous: bool,
+            observ_dim: int,
+            action_dim: int,
+            action_scaling: float = None,
+            lr: float = 0.001,
+            k_epochs: int = 7,
+            policy_clip: float = 0.2,
+            GAE_lambda: float = 0.95,
+            gamma: float = 0.995,
+            batch_size: int = 1024,
+            mini_batch_size: int = 64,
+            use_RND: bool = False,
+            beta: int = 0.001
+    ):
+        self.device = require_cuda()
+        self.policy = ActorCritic(is_continuous, observ_dim, action_dim)
+        self.policy_old = ActorCritic(is_continuous, observ_dim, action_dim)
+        if use_RND:
+            self.rnd = RND(in_features=observ_dim, out_features=observ_dim, beta=beta)
+
+        self.memory = Memory()
+        self.policy_old.flat.copy_(self.policy.flat)  # policy_old.load_state_dict(policy.state_dict())  PPO.py:44
+        self.policy.train()
+        self.policy_old.eval()
+
+        self.loss_fn = nn.SmoothL1Loss()  # API attribute; the fused kernel evaluates SmoothL1(mean, beta=1) itself
+        self.optimizer = FusedAdamW(self.policy.flat, lr=lr, weight_decay=0.01, max_norm=2.0)
+
+        self.is_continuous = is_continuous
+        self.action_scaling = action_scaling
+        self.use_RND = use_RND
+        self.beta = beta
+        self.lr = lr
+        self.policy_clip = policy_clip
+        self.k_epochs = k_epochs
+        self.GAE_lambda = GAE_lambda
+        self.gamma = gamma
+        self.batch_size = batch_size
+        self.mini_batch_size = mini_batch_size
+        self.observ_dim = observ_dim
+        self.action_dim = action_dim
+
+        # sampling: counter-based Philox keyed by (seed; row, call) - the seed comes from torch's global generator so
+        # that torch.manual_seed(...) makes runs repeatable, like the reference's dist.sample()
+        self._seed = int(t.randint(0, 2 ** 62, (1,)).item())
+        self._calls = 0
+        # progress / loss reporting: the reference syncs once per minibatch for the tqdm label (PPO.py:254-255)
+        self.show_progress = True
+        self.report_loss = False
+        self.last_losses = None   # device [steps, 4] float64: sums of (policy term, SmoothL1 term, entropy), rows
+        self._grad = t.zeros_like(self.policy.flat)
+        self._ws = None
+
+    # ------------------------------------------------------------------------------------------------ acting
+    def _action_scale(self) -> float:
+        if not self.is_continuous:
+            return 1.0
+        if self.action_scaling is None:
+            raise TypeError("continuous PPO needs action_scaling (the reference multiplies tanh(action) by it)")
+        return float(self.action_scaling)
+
+    @t.no_grad()
+    def get_action_device(self, states: t.Tensor, row_ids: t.Tensor | None = None, call_index: int | None = None) -> t.Tensor:
+        """Actions for `states` [n, O] (CUDA float32) as a CUDA tensor: int64 [n] / float32 [n, A]."""
+        if call_index is None:
+            call_index = self._calls
+            self._calls += 1
+        return ops.policy_act(self.policy_old.flat, self.is_continuous, self.observ_dim, self.action_dim, self._action_scale(),
+                              states, self._seed, call_index, row_ids=row_ids)
+
+    @t.no_grad()
+    def get_action(self, state: t.Tensor, _row_ids: t.Tensor | None = None, _call_index: int | None = None) -> np.ndarray:
+        """PPO.py:82-96: host tensor of any float dtype in, host numpy out."""
+        state = state.to(dtype=t.float32, device=self.device).reshape(-1, self.observ_dim).contiguous()
+        return self.get_action_device(state, _row_ids, _call_index).cpu().numpy()
+
+    def batch_packer(self, values, batch_size: int):
+        """PPO.py:98-105: sequential chunks (what list(DataLoader(tensor, batch_size)) yields)."""
+        if isinstance(values, t.Tensor):
+            batch = list(t.split(values, batch_size))
+        elif isinstance(values, list):
+            batch = [list(t.split(value, batch_size)) for value in values]
+        return batch
+
+    # ------------------------------------------------------------------------------------------------ GAE
+    def compute_gae(self, rewards: np.ndarray, dones: np.ndarray, state_values: np.ndarray, next_value: np.ndarray):
+        """PPO.py:107-120 on the device (prl_gae: float32, the reference's operation order); returns a list."""
+        dev = lambda x: t.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))).to(self.device)  # noqa: E731
+        nv = dev(np.asarray(next_value, dtype=np.float32).reshape(-1)[:1])
+        out = ops.gae(dev(rewards), dev(dones), dev(state_values), self.gamma, self.GAE_lambda, next_value=nv)
+        return list(out.cpu().numpy())
+
+    # ------------------------------------------------------------------------------------------------ learn
+    @t.no_grad()
+    def learn(self):
+        if len(self.memory.states) < self.batch_size:
+            return
+        O, A, cont = self.observ_dim, self.action_dim, self.is_continuous
+        AW = A if cont else 1
+        states, actions, rewards, dones = self.memory.device_view(O, AW, self.device)
+        N = states.shape[0]
+        mb = int(self.mini_batch_size)
+        comm = pdist.active()
+
+        # old-policy evaluation (PPO.py:134-154): row-independent, so one launch over all N rows
+        old_logp, old_values, _ = ops.policy_evaluate(self.policy_old.flat, cont, O, A, states, actions)
+
+        if self.use_RND:  # PPO.py:157-178: rewards + intrinsic, THEN one predictor pass over the same chunks
+            rewards = self.rnd.intrinsic_reward_device(states, add_to=rewards)
+            for i in range(0, N, mb):
+                self.rnd.update_pred_chunk(states[i:i + mb])
+        self.memory.clear()  # PPO.py:184 (the device rows stay valid until the next transfer)
+
+        returns = ops.gae(rewards, dones, old_values, self.gamma, self.GAE_lambda)  # next_value = V(last stored state)
+        # advantages = returns - values; (adv - mean) / (std + 1e-8) over ALL rows of ALL ranks (PPO.py:198-199)
+        _, stats = ops.adv_normalize(returns, old_values, phase=1)
+        if comm is not None:
+            comm.allreduce_(stats)
+        adv, _ = ops.adv_normalize(returns, old_values, stats=stats, phase=2)
+
+        # minibatch schedule: sequential chunks of the flat env-major buffer, same order every epoch (PPO.py:202-211).
+        # Sharded: global minibatch k = union of every rank's k-th local chunk.
+        if comm is not None:
+            mb_local, n_mb, counts = pdist.minibatch_schedule(comm.allgather_int(N), mb)
+        else:
+            mb_local, n_mb = mb, -(-N // mb)
+            counts = [min(N - k * mb, mb) for k in range(n_mb)]
+
+        need = ops.update_ws_floats(cont, O, A, min(mb_local, N))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = t.empty(need, dtype=t.float32, device=self.device)
+        steps = self.k_epochs * n_mb
+        self.last_losses = t.zeros(steps, 4, dtype=t.float64, device=self.device)
+        pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
+        step = 0
+        for _ in range(self.k_epochs):
+            for k in range(n_mb):
+                lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
+                if hi > lo:
+                    ops.ppo_grad(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
+                                 returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, self.last_losses[step], self._ws)
+                else:
+                    self._grad.zero_()  # this rank has no rows in minibatch k; it still joins the allreduce
+                if comm is not None:
+                    comm.allreduce_(self._grad)
+                self.optimizer.step(self._grad)
+                if pbar is not None:
+                    pbar.update(hi - lo)
+                    if self.report_loss:
+                        l = self.last_losses[step].cpu().numpy()
+                        pbar.set_description(f"Loss: {(l[0] + 0.5 * l[1] - 0.01 * l[2]) / max(l[3], 1.0): .6f}")
+                step += 1
+        if pbar is not None:
+            pbar.close()
+        self.policy_old.flat.copy_(self.policy.flat)  # PPO.py:258-260
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def load_weights(self, path: str):
+        """PPO.py:262-277: same files and state_dict keys as the reference; a missing file is ignored."""
+        try:
+            self.policy.load_state_dict(t.load(path + '/Policy_weights.pth', weights_only=True, map_location=self.device))
+            self.policy_old.flat.copy_(self.policy.flat)
+            if self.use_RND:
+                self.rnd.load_state_dict(t.load(path + '/RND_weights.pth', weights_only=True, map_location=self.device))
+        except FileNotFoundError:
+            pass
+
+    def save_weights(self, path: str):
+        t.save(self.policy.state_dict(), path + '/Policy_weights.pth')
+        if self.use_RND:
+            t.save(self.rnd.state_dict(), path + '/RND_weights.pth')

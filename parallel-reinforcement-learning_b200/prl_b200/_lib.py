@@ -75,12 +75,58 @@ def load_library(path: str | None = None):
     return lib
 
 
+def require_cuda():
+    """The torch device the kernels run on.  Raises (no CPU fallback) when the library or a CUDA device is missing."""
+    import torch
+
+    load_library()
+    if not torch.cuda.is_available():
+        raise PrlError("prl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# kernels launched by one call of each entry point (csrc/*.cu) - used to count launches, e.g. by bench.py
+KERNELS_PER_CALL = {
+    "prl_test_sincos": 1, "prl_test_pow2": 1, "prl_test_philox": 1, "prl_env_reset": 1, "prl_env_set_state": 1,
+    "prl_env_get_state": 1, "prl_env_step": 1, "prl_compact_indices": 2, "prl_gather_rows": 1, "prl_mask_update": 1,
+    "prl_buffer_append": 1, "prl_buffer_transfer": 7, "prl_policy_act": 1, "prl_policy_evaluate": 1, "prl_rollout": 1,
+    "prl_gae": 3, "prl_gae_columns": 1, "prl_adv_normalize": 1, "prl_ppo_grad": 2, "prl_adamw_step": 1,
+    "prl_rnd_intrinsic": 1, "prl_rnd_grad": 2,
+}
+CALL_COUNTS: dict[str, int] = {}
+_profile = None  # name -> [(start event, end event)] while profile_calls() is active
+
+
+def profile_calls(enable: bool):
+    """Time every entry-point call with CUDA events on the current (= launching) stream.  Returns the previous
+    record: {name: [(torch.cuda.Event, torch.cuda.Event), ...]}."""
+    global _profile
+    prev = _profile
+    _profile = {} if enable else None
+    return prev
+
+
 def call(name: str, *args):
     """Invoke a status-returning entry point; raise PrlError with prl_last_error() on failure."""
     lib = load_library()
-    rc = getattr(lib, name)(*args)
+    CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
+    if _profile is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _profile.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise PrlError(f"{name} failed ({rc}): {lib.prl_last_error().decode()}")
+
+
+def launches(counts: dict[str, int] | None = None) -> int:
+    counts = CALL_COUNTS if counts is None else counts
+    return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in counts.items())
 
 
 def fn(name: str):

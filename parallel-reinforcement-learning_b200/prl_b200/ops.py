@@ -33,6 +33,14 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def policy_param_count(is_continuous, O, A):
+    return int(_lib.fn("prl_policy_param_count")(int(is_continuous), int(O), int(A)))
+
+
+def rnd_param_count(I, Oo):
+    return int(_lib.fn("prl_rnd_param_count")(int(I), int(Oo)))
+
+
 # ------------------------------------------------------------------------------------------------ test hooks
 def test_sincos(x):
     s, c = torch.empty_like(x), torch.empty_like(x)

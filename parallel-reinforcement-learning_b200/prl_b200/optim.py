@@ -1,0 +1,38 @@
+"""clip_grad_norm_ + AdamW as ONE kernel over the flat parameter buffer (csrc/update.cu::k_adamw).
+
+Reference: `optim.AdamW(policy.parameters(), lr)` with torch defaults betas (0.9, 0.999), eps 1e-8, weight_decay 0.01
+(/root/reference/PPO/PPO.py:53-56) and `nn.utils.clip_grad_norm_(policy.parameters(), 2.0)` (:250); RND's optimiser at
+/root/reference/PPO/RND.py:46-49 (lr 1e-3, no clipping).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdamW:
+    def __init__(self, flat_params: torch.Tensor, lr: float, weight_decay: float = 0.01, max_norm: float = 2.0):
+        self.params = flat_params
+        self.lr, self.weight_decay, self.max_norm = float(lr), float(weight_decay), float(max_norm)
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+        self.step_count = 0
+        self.grad_norm = torch.zeros(1, dtype=torch.float64, device=flat_params.device)  # last pre-clip norm
+
+    def step(self, grad: torch.Tensor) -> None:
+        self.step_count += 1
+        ops.adamw_step(self.params, grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.weight_decay,
+                       self.max_norm, self.grad_norm)
+
+    def zero_grad(self, set_to_none: bool = True) -> None:  # API compatibility: gradients are produced whole by the kernels
+        pass
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "weight_decay": self.weight_decay, "max_norm": self.max_norm}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

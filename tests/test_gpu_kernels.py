@@ -54,6 +54,19 @@ def test_device_sincos_equals_libm(ops):
     assert np.array_equal(bits(c.cpu().numpy()), bits(np.cos(x)))
 
 
+def test_device_pow2_equals_libm(ops):
+    """pow(x, 2.0) / powf(x, 2.0f) as numpy scalars evaluate `x ** 2` (csrc/pow_glibc.cuh) - not always x*x."""
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(lo, hi, 300_000) for lo, hi in [(-1e-7, 1e-7), (-0.1, 0.1), (-1, 1), (0.99, 1.01), (-3.2, 3.2),
+                                                                   (-8, 8), (-30, 30), (-1e6, 1e6)]] + [np.array([0.0, -0.0, 1.0, -1.0, 2.0])])
+    xf = x.astype(np.float32)
+    want64, want32 = cref.pow2(x, xf)
+    assert (want64 != x * x).sum() > 100  # the case this exists for
+    got64, got32 = ops.test_pow2(dev(x), dev(xf))
+    assert np.array_equal(bits(got64.cpu().numpy()), bits(want64))
+    assert np.array_equal(bits(got32.cpu().numpy()), bits(want32))
+
+
 def test_philox_matches_host_restatement(ops):
     for seed, c in [(0, (0, 0, 0, 0)), (0x123456789ABCDEF, (7, 11, 13, 17)), (2**64 - 1, (2**32 - 1, 5, 2**31, 9))]:
         assert np.array_equal(ops.test_philox(seed, *c), philox_np(seed, *c))
@@ -266,25 +279,33 @@ def test_ppo_grad_and_adamw_match_reference_single_step(ops, golden, name, roll)
     grad = t.zeros_like(params); loss = t.zeros(4, dtype=t.float64, device="cuda")
     ws = t.empty(ops.update_ws_floats(cont, O, A, N), device="cuda")
     ops.ppo_grad(params, cont, O, A, s, a, logp, adv, ret, float(g["policy_clip"]), 1.0 / N, grad, loss, ws)
-    # oracle gradient (torch autograd on the CPU restatement)
-    p = oppo.unflatten(g["init_flat"], cont, O, A)
+    # oracle gradient: torch autograd on the CPU restatement, in float64 (the truth) and float32 (what the reference runs)
     keys = oppo.param_keys(cont)
-    for k in keys:
-        p[k].requires_grad_(True)
-    old_lp = t.from_numpy(g["eval_logp"])
-    lo = oppo.ppo_loss(p, cont, t.from_numpy(r["states"]), t.from_numpy(r["actions"]), old_lp, t.from_numpy(g["advantages"]),
-                       t.from_numpy(g["gae_returns"]), float(g["policy_clip"]))
-    want = t.cat([x.reshape(-1) for x in t.autograd.grad(lo, [p[k] for k in keys])]).numpy()
-    got = grad.cpu().numpy()
+
+    def oracle_grad(dtype):
+        p = {k: v.to(dtype).requires_grad_(True) for k, v in oppo.unflatten(g["init_flat"], cont, O, A).items()}
+        c = lambda x: t.from_numpy(np.asarray(x)).to(dtype)  # noqa: E731
+        lo = oppo.ppo_loss(p, cont, c(r["states"]), c(r["actions"]), c(g["eval_logp"]), c(g["advantages"]), c(g["gae_returns"]),
+                           float(g["policy_clip"]))
+        return lo.detach(), t.cat([x.reshape(-1) for x in t.autograd.grad(lo, [p[k] for k in keys])]).double().numpy()
+
+    lo, want = oracle_grad(t.float64)
+    _, want32 = oracle_grad(t.float32)
+    got = grad.cpu().numpy().astype(np.float64)
     scale = np.abs(want).max()
-    assert np.abs(got - want).max() <= 1e-5 * scale + 1e-7, (np.abs(got - want).max(), scale)
+    err, err32 = np.abs(got - want).max() / scale, np.abs(want32 - want).max() / scale
+    # float32 conditioning: ratio = exp(logp - old_logp) carries ulp(|logp|) ~ 1e-6 absolute noise per row and the
+    # Gaussian log-density amplifies it by (z^2 - 1) / sigma, so torch's own float32 autograd sits 3e-7 (discrete) to
+    # 1e-5 (continuous) away from the float64 gradient on these fixtures.  Bar: within 3e-5 of the float64 truth
+    # relative to the largest component, and no worse than 4x torch-float32's own distance + 1e-6.
+    assert err <= 3e-5 and err <= 4 * err32 + 1e-6, (err, err32)
     l = loss.cpu().numpy()
     total = l[0] / N + 0.5 * l[1] / N - 0.01 * l[2] / N
-    assert total == pytest.approx(float(lo), rel=1e-5)
+    assert total == pytest.approx(float(lo), rel=1e-5)  # loss: 1e-5 relative (north_star)
     m = t.zeros_like(params); v = t.zeros_like(params)
     ops.adamw_step(params, grad, m, v, 1, float(g["lr"]))
     np.testing.assert_allclose(params.cpu().numpy(), g["post_flat"], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(m.cpu().numpy(), g["post_exp_avg"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(m.cpu().numpy(), g["post_exp_avg"], rtol=1e-4, atol=1e-5 * np.abs(g["post_exp_avg"]).max())
 
 
 def test_rnd_intrinsic_and_grad_match_reference(ops, golden):
