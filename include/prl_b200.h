@@ -46,6 +46,11 @@ size_t prl_scan_ws_bytes(int64_t n);
 int prl_test_sincos(const double *x, double *sin_out, double *cos_out, int64_t n, void *stream);
 int prl_test_pow2(const double *x, double *out, const float *xf, float *outf, int64_t n, void *stream);
 int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
+/* tensor-core building blocks (csrc/umma.cuh): one 128-row tile, tcgen05.mma kind::tf32 from shared memory.
+ * mode 0: D[128][128] = A[128][64] B[128][64]^T; 1: D[128][64] = A[128][64] B[64:128][0:64]; 2: D[128][64] =
+ * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[13]
+ * (see csrc/umma_test.cu).  *status != 0: the MMA never completed. */
+int prl_test_umma(int mode, const float *A, const float *B, float *D, int *status, const int32_t *cfg_host, void *stream);
 
 /* ---------------------------------------------------------------- EnvVectorizer (AsyncTools/AsyncPPO.py:35-102) */
 /* reset(): AsyncPPO.py:48-62.  Draws every env's start state from Philox(seed, episode) in the env's reset box,

@@ -62,6 +62,16 @@ def test_philox(seed, c0, c1, c2, c3):
     return out.cpu().numpy().view("uint32")
 
 
+def test_umma(mode, A, B, cfg=None):
+    n_out = {0: 128, 1: 64, 2: 64, 3: 16}[mode] if cfg is None else cfg[2]
+    D = torch.full((128, n_out), float("nan"), dtype=torch.float32, device=_dev())
+    status = torch.zeros(1, dtype=torch.int32, device=_dev())
+    cfg_arr = (C.c_int32 * 13)(*[int(x) for x in cfg]) if cfg is not None else None
+    call("prl_test_umma", -1 if cfg is not None else mode, _ptr(A, torch.float32), _ptr(B, torch.float32), _ptr(D), _ptr(status),
+         cfg_arr, _stream())
+    return D, int(status.item())
+
+
 # ------------------------------------------------------------------------------------------------ env state
 class EnvState:
     """Device-resident state of E copies of one classic-control env: SoA fp64 [S][E], TimeLimit counters,

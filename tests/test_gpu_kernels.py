@@ -67,6 +67,24 @@ def test_device_pow2_equals_libm(ops):
     assert np.array_equal(bits(got32.cpu().numpy()), bits(want32))
 
 
+def test_tensor_core_building_blocks_exact(ops):
+    """tcgen05.mma kind::f16 (bf16 operands) over the row-per-thread shared-memory layout, in the four operand-major combinations the
+    fused update uses.  Inputs are small dyadic rationals (exact in bf16), so the fp32 accumulators must be EXACT."""
+    rng = np.random.default_rng(8)
+    q = lambda *shape: (rng.integers(-16, 17, shape) / 8.0).astype(np.float32)  # noqa: E731
+    A, W = q(128, 64), q(128, 64)
+    D, st = ops.test_umma(0, dev(A), dev(W))
+    assert st == 0 and np.array_equal(D.cpu().numpy(), A @ W.T)
+    D, st = ops.test_umma(1, dev(A), dev(W))
+    assert st == 0 and np.array_equal(D.cpu().numpy(), A @ W[64:])
+    Z, F = q(128, 128), q(128, 64)
+    D, st = ops.test_umma(2, dev(Z), dev(F))
+    assert st == 0 and np.array_equal(D.cpu().numpy(), Z.T @ F)
+    X = q(128, 16)
+    D, st = ops.test_umma(3, dev(Z), dev(X))
+    assert st == 0 and np.array_equal(D.cpu().numpy(), Z.T @ X)
+
+
 def test_philox_matches_host_restatement(ops):
     for seed, c in [(0, (0, 0, 0, 0)), (0x123456789ABCDEF, (7, 11, 13, 17)), (2**64 - 1, (2**32 - 1, 5, 2**31, 9))]:
         assert np.array_equal(ops.test_philox(seed, *c), philox_np(seed, *c))
