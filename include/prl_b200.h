@@ -143,6 +143,18 @@ int prl_ppo_grad(const float *params, int is_continuous, int obs_dim, int action
                  const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
                  float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
                  void *stream);
+/* Tensor-core form of prl_ppo_grad (csrc/update_tc.cu): same contract and gradient layout; tcgen05.mma (bf16x3 split
+ * operands, fp32 accumulation in tensor memory) for every contraction over features or rows.  Discrete policies with
+ * observ_dim <= 16 and action_dim <= 8 (prl_ppo_grad_tc_supported).  prl_ppo_grad_tc_status (host-synchronising)
+ * reports 1 if a tensor-core phase never completed. */
+int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim);
+size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch);
+int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
+                    const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
+                    float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
+                    void *stream);
+int prl_ppo_grad_tc_status(const float *ws, int is_continuous, int obs_dim, int action_dim, int64_t batch,
+                           int *status_host, void *stream);
 /* nn.utils.clip_grad_norm_(params, max_norm) + AdamW.step (PPO.py:250-252; torch defaults betas (0.9,0.999),
  * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,

@@ -247,6 +247,28 @@ def ppo_grad(params, is_continuous, O, A, states, actions, old_logp, adv, return
          _ptr(ws, torch.float32), ws.numel(), _stream())
 
 
+def tc_supported(is_continuous, O, A):
+    return bool(_lib.fn("prl_ppo_grad_tc_supported")(int(is_continuous), int(O), int(A)))
+
+
+def update_tc_ws_floats(is_continuous, O, A, batch):
+    return int(_lib.fn("prl_update_tc_ws_floats")(int(is_continuous), O, A, batch))
+
+
+def ppo_grad_tc(params, is_continuous, O, A, states, actions, old_logp, adv, returns, policy_clip, inv_count, grad, loss_out, ws):
+    b = states.shape[0]
+    call("prl_ppo_grad_tc", _ptr(params, torch.float32), int(is_continuous), O, A, _ptr(states, torch.float32),
+         _ptr(actions, torch.float32), _ptr(old_logp, torch.float32), _ptr(adv, torch.float32), _ptr(returns, torch.float32),
+         b, float(policy_clip), float(inv_count), _ptr(grad, torch.float32), _ptr(loss_out, torch.float64),
+         _ptr(ws, torch.float32), ws.numel(), _stream())
+
+
+def ppo_grad_tc_status(ws, is_continuous, O, A, batch):
+    st = C.c_int(0)
+    call("prl_ppo_grad_tc_status", _ptr(ws, torch.float32), int(is_continuous), O, A, batch, C.byref(st), _stream())
+    return st.value
+
+
 def adamw_step(params, grad, exp_avg, exp_avg_sq, step, lr, weight_decay=0.01, max_norm=2.0, grad_norm_out=None):
     call("prl_adamw_step", _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
          _ptr(exp_avg_sq, torch.float32), params.numel(), int(step), float(lr), float(weight_decay), float(max_norm),

@@ -326,6 +326,80 @@ def test_ppo_grad_and_adamw_match_reference_single_step(ops, golden, name, roll)
     np.testing.assert_allclose(m.cpu().numpy(), g["post_exp_avg"], rtol=1e-4, atol=1e-5 * np.abs(g["post_exp_avg"]).max())
 
 
+@pytest.mark.parametrize("name,roll", [("discrete_1step", "cartpole"), ("discrete", "cartpole"), ("rnd", "acrobot")])
+def test_tensor_core_ppo_grad_matches_oracle(ops, golden, name, roll):
+    """The tcgen05 update kernel (prl_ppo_grad_tc) against the float64 oracle gradient and the fp32-FMA kernel: same bar
+    as the fp32 path (3e-5 of the largest component, no worse than 4x torch-float32's own distance)."""
+    g, r = golden("learn_" + name), golden("rollout_" + roll)
+    cont, O, A = bool(g["is_continuous"]), int(g["O"]), int(g["A"])
+    assert ops.tc_supported(cont, O, A)
+    N = len(r["states"])
+    params = dev(g["init_flat"])
+    s = dev(r["states"]); a = dev(r["actions"].reshape(N, -1))
+    rng = np.random.default_rng(11)
+    old_lp = g["eval_logp"] + rng.normal(0, 0.05, N).astype(np.float32)        # ratios away from 1: exercises the clip branches
+    adv_np = rng.standard_normal(N).astype(np.float32); ret_np = rng.standard_normal(N).astype(np.float32)
+    keys = oppo.param_keys(cont)
+
+    def oracle_grad(dtype):
+        p = {k: v.to(dtype).requires_grad_(True) for k, v in oppo.unflatten(g["init_flat"], cont, O, A).items()}
+        c = lambda x: t.from_numpy(np.asarray(x)).to(dtype)  # noqa: E731
+        lo = oppo.ppo_loss(p, cont, c(r["states"]), c(r["actions"]), c(old_lp), c(adv_np), c(ret_np), 0.2)
+        return lo.detach(), t.cat([x.reshape(-1) for x in t.autograd.grad(lo, [p[k] for k in keys])]).double().numpy()
+
+    lo, want = oracle_grad(t.float64)
+    _, want32 = oracle_grad(t.float32)
+    grads = {}
+    for path in ("tc", "fp32"):
+        grad = t.full_like(params, float("nan")); loss = t.zeros(4, dtype=t.float64, device="cuda")
+        if path == "tc":
+            ws = t.empty(ops.update_tc_ws_floats(cont, O, A, N), device="cuda")
+            ops.ppo_grad_tc(params, cont, O, A, s, a, dev(old_lp), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
+            assert ops.ppo_grad_tc_status(ws, cont, O, A, N) == 0
+        else:
+            ws = t.empty(ops.update_ws_floats(cont, O, A, N), device="cuda")
+            ops.ppo_grad(params, cont, O, A, s, a, dev(old_lp), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
+        grads[path] = grad.cpu().numpy().astype(np.float64)
+        l = loss.cpu().numpy()
+        assert (l[0] + 0.5 * l[1] - 0.01 * l[2]) / N == pytest.approx(float(lo), rel=1e-5, abs=1e-6), path
+    scale = np.abs(want).max()
+    err32 = np.abs(want32 - want).max() / scale
+    for path, got in grads.items():
+        off = 0
+        for k, n in zip(keys, [int(np.prod(oppo.param_shapes(cont, O, A)[k])) for k in keys]):   # per-block report on failure
+            blk = np.abs(got[off:off + n] - want[off:off + n]).max() / scale
+            assert blk <= 3e-5 and blk <= 4 * err32 + 1e-6, (path, k, blk, err32)
+            off += n
+
+
+def test_tensor_core_ppo_grad_large_batch_matches_fp32_kernel(ops, golden):
+    """65 537 rows: many tiles per CTA (tensor-memory accumulation across tiles), a ragged last tile, both kernels on
+    the same random inputs.  Bar: 3e-5 of the largest gradient component."""
+    g = golden("learn_discrete")
+    O, A, N = 4, 2, 65537
+    rng = np.random.default_rng(12)
+    params = dev(g["init_flat"])
+    s = dev(rng.uniform(-1, 1, (N, O)).astype(np.float32)); a = dev(rng.integers(0, A, (N, 1)).astype(np.float32))
+    logp, _, _ = ops.policy_evaluate(params, False, O, A, s, a)
+    old_lp = logp + dev(rng.normal(0, 0.1, N).astype(np.float32))
+    adv = dev(rng.standard_normal(N).astype(np.float32)); ret = dev(rng.standard_normal(N).astype(np.float32))
+    out = {}
+    for path in ("tc", "fp32"):
+        grad = t.full_like(params, float("nan")); loss = t.zeros(4, dtype=t.float64, device="cuda")
+        if path == "tc":
+            ws = t.empty(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
+            ops.ppo_grad_tc(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
+            assert ops.ppo_grad_tc_status(ws, False, O, A, N) == 0
+        else:
+            ws = t.empty(ops.update_ws_floats(False, O, A, N), device="cuda")
+            ops.ppo_grad(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
+        out[path] = (grad.cpu().numpy().astype(np.float64), loss.cpu().numpy())
+    gt, gf = out["tc"][0], out["fp32"][0]
+    assert np.isfinite(gt).all()
+    assert np.abs(gt - gf).max() <= 3e-5 * np.abs(gf).max(), (np.abs(gt - gf).max(), np.abs(gf).max())
+    np.testing.assert_allclose(out["tc"][1], out["fp32"][1], rtol=1e-6)
+
+
 def test_rnd_intrinsic_and_grad_match_reference(ops, golden):
     g, r = golden("learn_rnd"), golden("rollout_acrobot")
     O = int(g["O"])
