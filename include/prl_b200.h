@@ -48,7 +48,7 @@ int prl_test_pow2(const double *x, double *out, const float *xf, float *outf, in
 int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
 /* tensor-core building blocks (csrc/umma.cuh): one 128-row tile, tcgen05.mma kind::tf32 from shared memory.
  * mode 0: D[128][128] = A[128][64] B[128][64]^T; 1: D[128][64] = A[128][64] B[64:128][0:64]; 2: D[128][64] =
- * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[13]
+ * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[16]
  * (see csrc/umma_test.cu).  *status != 0: the MMA never completed. */
 int prl_test_umma(int mode, const float *A, const float *B, float *D, int *status, const int32_t *cfg_host, void *stream);
 
@@ -145,16 +145,16 @@ int prl_ppo_grad(const float *params, int is_continuous, int obs_dim, int action
                  void *stream);
 /* Tensor-core form of prl_ppo_grad (csrc/update_tc.cu): same contract and gradient layout; tcgen05.mma (bf16x3 split
  * operands, fp32 accumulation in tensor memory) for every contraction over features or rows.  Discrete policies with
- * observ_dim <= 16 and action_dim <= 8 (prl_ppo_grad_tc_supported).  prl_ppo_grad_tc_status (host-synchronising)
- * reports 1 if a tensor-core phase never completed. */
+ * observ_dim <= 16 and action_dim <= 8 (prl_ppo_grad_tc_supported).  The workspace must be zeroed once before its first
+ * use: ws[0] is a sticky status word that prl_ppo_grad_tc_status (host-synchronising) reads - 1 if a tensor-core phase
+ * of any call never completed. */
 int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim);
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch);
 int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
                     const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
                     float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
                     void *stream);
-int prl_ppo_grad_tc_status(const float *ws, int is_continuous, int obs_dim, int action_dim, int64_t batch,
-                           int *status_host, void *stream);
+int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream);
 /* nn.utils.clip_grad_norm_(params, max_norm) + AdamW.step (PPO.py:250-252; torch defaults betas (0.9,0.999),
  * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,

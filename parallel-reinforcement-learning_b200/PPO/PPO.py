@@ -83,6 +83,9 @@ class PPO:
         self.last_losses = None   # device [steps, 4] float64: sums of (policy term, SmoothL1 term, entropy), rows
         self._grad = t.zeros_like(self.policy.flat)
         self._ws = None
+        # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies), "fp32" = CUDA-core
+        # FMA kernel (csrc/update_ppo.cu; every configuration).  Same math and tolerances, two members of one family.
+        self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
 
     # ------------------------------------------------------------------------------------------------ acting
     def _action_scale(self) -> float:
@@ -159,9 +162,13 @@ class PPO:
             mb_local, n_mb = mb, -(-N // mb)
             counts = [min(N - k * mb, mb) for k in range(n_mb)]
 
-        need = ops.update_ws_floats(cont, O, A, min(mb_local, N))
+        use_tc = self.update_path == "tensor"
+        if use_tc and not ops.tc_supported(cont, O, A):
+            raise ValueError("update_path='tensor' supports discrete policies with observ_dim <= 16 and action_dim <= 8")
+        grad_fn = ops.ppo_grad_tc if use_tc else ops.ppo_grad
+        need = (ops.update_tc_ws_floats if use_tc else ops.update_ws_floats)(cont, O, A, min(mb_local, N))
         if self._ws is None or self._ws.numel() < need:
-            self._ws = t.empty(need, dtype=t.float32, device=self.device)
+            self._ws = t.zeros(need, dtype=t.float32, device=self.device)
         steps = self.k_epochs * n_mb
         self.last_losses = t.zeros(steps, 4, dtype=t.float64, device=self.device)
         pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
@@ -170,7 +177,7 @@ class PPO:
             for k in range(n_mb):
                 lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
                 if hi > lo:
-                    ops.ppo_grad(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
+                    grad_fn(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
                                  returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, self.last_losses[step], self._ws)
                 else:
                     self._grad.zero_()  # this rank has no rows in minibatch k; it still joins the allreduce
@@ -185,6 +192,8 @@ class PPO:
                 step += 1
         if pbar is not None:
             pbar.close()
+        if use_tc and ops.ppo_grad_tc_status(self._ws) != 0:
+            raise RuntimeError("tensor-core update: an MMA phase never completed (mbarrier timeout)")
         self.policy_old.flat.copy_(self.policy.flat)  # PPO.py:258-260
 
     # ------------------------------------------------------------------------------------------------ checkpoints

@@ -37,6 +37,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// same with a swizzle mode in bits [61,64): 0 none, 2 = 128-byte swizzle, 4 = 64-byte, 6 = 32-byte
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)layout_type << 61);
+}
 // 32-bit instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate.  a_mn / b_mn: 1 = MN-major, 0 = K-major.
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -92,6 +96,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
         if (ok) return true;
     }
     return false;
+}
+
+// one lane of the (converged) warp; the rest of the warp skips the guarded block
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- MMA ---------------------------------------------------------------------------------------------------------

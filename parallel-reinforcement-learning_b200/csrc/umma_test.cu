@@ -18,12 +18,26 @@ __device__ __forceinline__ void stage_rows(unsigned char *dst, const float *__re
     }
 }
 
-// Generic driver: cfg = {a_cols, b_cols, n_out, idesc, nsteps, a_off, a_step, a_lbo, a_sbo, b_off, b_step, b_lbo, b_sbo}
-// (bytes); A is staged as [128][a_cols], B as [128][b_cols]; K-step s uses descriptors at off + s * step.
+// stage as bf16 into 128-byte rows with the 128B swizzle: byte(r, c) = r * 128 + (((c / 8) ^ (r % 8)) * 16) + (c % 8) * 2 within
+// each [128][64] block (blocks of 64 columns are 16 KB apart); the base must be 1024-byte aligned
+__device__ __forceinline__ void stage_rows_sw128(unsigned char *dst, const float *__restrict__ src, int cols) {
+    const int r = threadIdx.x;
+    for (int c = 0; c < cols; c += 8) {
+        const float4 a = *reinterpret_cast<const float4 *>(src + (size_t)r * cols + c);
+        const float4 b = *reinterpret_cast<const float4 *>(src + (size_t)r * cols + c + 4);
+        const int blk = c / 64, ch = (c / 8) & 7;
+        *reinterpret_cast<uint4 *>(dst + blk * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+}
+
+// Generic driver: A is staged as [128][a_cols], B as [128][b_cols] (layout 0 = interleaved / no swizzle, 2 = 128-byte swizzled
+// rows); K-step s uses descriptors at off + s * step; the whole sequence is issued `reps` times (accumulating) and timed.
 struct UmmaTestCfg {
     int a_cols, b_cols, n_out;
     uint32_t idesc;
     int nsteps, a_off, a_step, a_lbo, a_sbo, b_off, b_step, b_lbo, b_sbo;
+    int a_layout, b_layout, reps;
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -35,8 +49,8 @@ k_test_umma(UmmaTestCfg c, const float *__restrict__ A, const float *__restrict_
     __shared__ uint32_t tmem_base_slot;
     const int warp = threadIdx.x >> 5;
 
-    stage_rows(sA, A, c.a_cols);
-    stage_rows(sB, B, c.b_cols);
+    if (c.a_layout == 2) stage_rows_sw128(sA, A, c.a_cols); else stage_rows(sA, A, c.a_cols);
+    if (c.b_layout == 2) stage_rows_sw128(sB, B, c.b_cols); else stage_rows(sB, B, c.b_cols);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -48,14 +62,33 @@ k_test_umma(UmmaTestCfg c, const float *__restrict__ A, const float *__restrict_
     fence_after_sync();
     const uint32_t tmem = tmem_base_slot;
 
-    if (threadIdx.x == 0) {
+    long long t0 = 0;
+    if (warp == 0) {   // warp-uniform control flow around the single issuing lane: descriptors stay in uniform registers
         const uint32_t a0 = smem_u32(sA) + c.a_off, b0 = smem_u32(sB) + c.b_off;
-        for (int s = 0; s < c.nsteps; ++s)
-            mma_bf16_ss(tmem, smem_desc(a0 + s * c.a_step, c.a_lbo, c.a_sbo), smem_desc(b0 + s * c.b_step, c.b_lbo, c.b_sbo), c.idesc, s > 0);
-        mma_commit(&bar);
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            da[s] = smem_desc_sw(a0 + s * c.a_step, c.a_lbo, c.a_sbo, c.a_layout);
+            db[s] = smem_desc_sw(b0 + s * c.b_step, c.b_lbo, c.b_sbo, c.b_layout);
+        }
+        const uint32_t idesc = c.idesc;
+        const int nsteps = c.nsteps;
+        t0 = clock64();
+        if (elect_one()) {
+            for (int rep = 0; rep < c.reps; ++rep) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (s < nsteps) mma_bf16_ss(tmem, da[s], db[s], idesc, (rep | s) != 0);
+            }
+            mma_commit(&bar);
+        }
+        __syncwarp();
     }
     const bool ok = mbar_wait(&bar, 0);
-    if (!ok && threadIdx.x == 0) *status = 1;
+    if (threadIdx.x == 0) {
+        status[1] = (int)(clock64() - t0);
+        if (!ok) status[0] = 1;
+    }
     fence_after_sync();
     for (int col = 0; col < c.n_out; col += 16) {
         float v[16];
@@ -79,19 +112,20 @@ extern "C" int prl_test_umma(int mode, const float *A, const float *B, float *D,
     constexpr int CH = umma::CHUNK;
     switch (mode) {
         // forward, two heads stacked along N: A, B K-major, 4 K-steps of 16 features
-        case 0: c = {64, 64, 128, idesc_bf16(128, 128, 0, 0), 4, 0, 2 * CH, CH, 128, 0, 2 * CH, CH, 128}; break;
+        case 0: c = {64, 64, 128, idesc_bf16(128, 128, 0, 0), 4, 0, 2 * CH, CH, 128, 0, 2 * CH, CH, 128, 0, 0, 1}; break;
         // dgrad of head 1: A K-major; B'[n' = k][K' = j] = W[64 + j][k] is the MN-major view of the same weight buffer
-        case 1: c = {64, 64, 64, idesc_bf16(128, 64, 0, 1), 4, 0, 2 * CH, CH, 128, 64 * 16, 256, 128, CH}; break;
+        case 1: c = {64, 64, 64, idesc_bf16(128, 64, 0, 1), 4, 0, 2 * CH, CH, 128, 64 * 16, 256, 128, CH, 0, 0, 1}; break;
         // weight gradient: contraction over the 128 rows, both operands MN-major, 8 K-steps of 16 rows
-        case 2: c = {128, 64, 64, idesc_bf16(128, 64, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH}; break;
-        case 3: c = {128, 16, 16, idesc_bf16(128, 16, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH}; break;
+        case 2: c = {128, 64, 64, idesc_bf16(128, 64, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1}; break;
+        case 3: c = {128, 16, 16, idesc_bf16(128, 16, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1}; break;
         default:
-            PRL_REQUIRE(cfg_host, "prl_test_umma: mode -1 needs cfg_host[13]");
+            PRL_REQUIRE(cfg_host, "prl_test_umma: mode -1 needs cfg_host[16]");
             c = {cfg_host[0], cfg_host[1], cfg_host[2], (uint32_t)cfg_host[3], cfg_host[4], cfg_host[5], cfg_host[6], cfg_host[7],
-                 cfg_host[8], cfg_host[9], cfg_host[10], cfg_host[11], cfg_host[12]};
+                 cfg_host[8], cfg_host[9], cfg_host[10], cfg_host[11], cfg_host[12], cfg_host[13], cfg_host[14], cfg_host[15]};
     }
     PRL_REQUIRE(c.a_cols % 8 == 0 && c.a_cols <= 128 && c.b_cols % 8 == 0 && c.b_cols <= 64 && c.n_out % 16 == 0 && c.n_out <= 128 &&
-                    c.nsteps >= 1 && c.nsteps <= 64, "prl_test_umma: configuration out of range");
+                    c.nsteps >= 1 && c.nsteps <= 8 && c.reps >= 1 && c.reps <= 4096 && (c.a_layout | c.b_layout | 2) == 2,
+                "prl_test_umma: configuration out of range");
     const size_t smem = 48 * 1024 + 1024;
     PRL_CUDA(cudaFuncSetAttribute(k_test_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_test_umma<<<1, 128, smem, (cudaStream_t)stream>>>(c, A, B, D, status);

@@ -4,23 +4,26 @@
 //
 // Reference: /root/reference/PPO/PPO.py:219-252 and PPO/ActorCritic.py:118-146.
 //
-// Work split.  One CTA = 128 threads = one 128-row tile at a time, persistent over tiles; thread r owns row r for all
-// per-row math (GroupNorm, SiLU, softmax / loss, their backward), held in registers.  Everything that contracts over
-// features or over rows runs as tcgen05.mma (kind::f16, bf16x3 split operands, fp32 accumulators in tensor memory):
+// Work split.  One CTA = 512 threads = one 128-row tile at a time, persistent over tiles.  Row r of the tile is owned
+// by FOUR threads (warps w, w+4, w+8, w+12 share a 32-row quarter; thread q of a row holds features 16q..16q+15 =
+// two GroupNorm groups), so every per-row array is 16 wide and lives in registers, and 16 warps per SM hide latency.
+// Everything that contracts over features or over rows runs as tcgen05.mma (kind::f16 on bf16x3 split operands, fp32
+// accumulators in tensor memory), issued by one elected lane of warp 0:
 //     forward   Z[r][(h,j)]  = sum_k F[r][k] W1_h[j][k]          M=128 N=128 K=64    (both heads in one GEMM)
 //     dgrad     DF[r][k]    += sum_j DZ_h[r][j] W1_h[j][k]       M=128 N=64  K=64    (B = MN-major view of the same W1 bytes)
 //     wgrad     DW_h[j][k]  += sum_r DZ_h[r][j] F[r][k]          M=128 N=64  K=128   (A, B = MN-major views of the same DZ / F bytes)
 //     wgrad0    DW0[j][i]   += sum_r DZ0[r][j] X[r][i]           M=128 N=16  K=128
 // The weight-gradient accumulators stay in tensor memory across ALL tiles of the CTA and are read out once.
-// What remains on the CUDA cores are the row-wise nonlinearities and the narrow column sums (GroupNorm affine and
-// output-layer gradients), done as warp butterfly reductions into per-warp register accumulators.
+// What remains on the CUDA cores are the row-wise nonlinearities (GroupNorm, SiLU, softmax / loss and their backward)
+// and the narrow column sums (GroupNorm affine and output-layer gradients), done as warp butterfly reductions into
+// per-warp register accumulators that are combined once at the end.
 #include "policy.cuh"
 #include "umma.cuh"
 
 namespace prl {
 using namespace umma;
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 512, TC_ROWS = 128, TC_W = 16;   // threads, rows per tile, features per thread
 constexpr int PIECE = 8 * CHUNK;     // one bf16 piece of a [128][64] matrix: 8 chunks x 2048 B = 16 KB
 constexpr int XPIECE = 2 * CHUNK;    // one bf16 piece of the [128][16] input matrix
 constexpr int TC_MAX_O = 16, TC_MAX_A = 8;
@@ -28,60 +31,59 @@ constexpr int TC_MAX_O = 16, TC_MAX_A = 8;
 // tensor-memory columns
 constexpr uint32_t TM_Z = 0, TM_DF = 128, TM_DW = 192 /* + 64 h */, TM_DW0 = 320, TM_COLS = 512;
 
-struct TcSmem {
-    unsigned char *W, *F, *DZ, *X;   // bf16 piece buffers: W 3 x PIECE (n = h*64 + j), F 3 x PIECE, DZ 4 x PIECE (p0 p1 p2 zero), X 3 x XPIECE
-    float *w0t, *g0w, *g0b;          // [O][64], [64], [64]
-    float *gw[2], *gb[2], *w2[2], *b2[2];
-    float *red;                      // [4 warps][NQ][64] final cross-warp combine
-};
-
-__host__ __device__ inline size_t tc_small_floats(const PolicyLayout &L) {
-    size_t n = (size_t)L.O * HID + 2 * HID;
-    for (int h = 0; h < 2; ++h) n += 2 * HID + (size_t)L.head[h].out * HID + round4(L.head[h].out);
+__host__ __device__ inline int tc_small_floats(const PolicyLayout &L) {
+    int n = L.O * HID + 2 * HID;
+    for (int h = 0; h < 2; ++h) n += 2 * HID + L.head[h].out * HID + round4(L.head[h].out);
     return n;
 }
 __host__ __device__ inline int tc_num_q(const PolicyLayout &L) { return 2 + 2 + L.head[0].out + 2 + L.head[1].out; }
-__host__ __device__ inline size_t tc_smem_bytes(const PolicyLayout &L) {
-    return 1024 + 3 * PIECE + 3 * PIECE + 4 * PIECE + 3 * XPIECE + tc_small_floats(L) * 4 + (size_t)4 * tc_num_q(L) * HID * 4 + 256;
+__host__ __device__ inline size_t tc_smem_bytes(const PolicyLayout &L, int NA) {
+    return 1024 + 3 * PIECE + 3 * PIECE + 4 * PIECE + 3 * XPIECE + (size_t)tc_small_floats(L) * 4 + (size_t)4 * TC_ROWS * NA * 4 +
+           (size_t)4 * tc_num_q(L) * HID * 4 + 256;
 }
 
-// write one row's 64 fp32 values as three bf16 pieces into a [128][64] piece-buffer triple (row-per-thread layout)
-__device__ __forceinline__ void store_row_pieces(unsigned char *base, int r, const float (&v)[HID]) {
+// ---- small math ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_sigmoid(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
+
+// write 16 fp32 values (features 16q..16q+15 of row r) as three bf16 pieces: chunks 2q, 2q+1 of a [128][64] piece triple
+__device__ __forceinline__ void store_pieces16(unsigned char *base, int r, int q, const float (&v)[TC_W]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 2; ++c) {
         uint32_t q0[4], q1[4], q2[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_bf16x3(v[8 * c + 2 * i], v[8 * c + 2 * i + 1], q0[i], q1[i], q2[i]);
-        unsigned char *p = base + c * CHUNK + r * 16;
+        unsigned char *p = base + (2 * q + c) * CHUNK + r * 16;
         *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
         *reinterpret_cast<uint4 *>(p + PIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
         *reinterpret_cast<uint4 *>(p + 2 * PIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
     }
 }
 
-// column sums over the warp's 32 rows: on return lane l holds the sums of features 2l and 2l+1 in v[0], v[1].
-// 5 exchange steps, 62 shuffles; v is consumed.
-__device__ __forceinline__ void warp_colsum64(float (&v)[HID], float &s0, float &s1) {
+// column sum of 8 per-row values over the warp's 32 rows: on return every lane holds the total of feature
+// f(lane) = 4*bit4 + 2*bit3 + bit2 of its lane index (4 lanes hold each feature).  9 shuffles.
+__device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
     const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int step = 0; step < 5; ++step) {
-        const int off = 16 >> step, n = 32 >> step;   // partner distance, surviving length
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            const float keep = up ? v[i + n] : v[i];
-            const float send = up ? v[i] : v[i + n];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    s0 = v[0];
-    s1 = v[1];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+    const float a0 = (u16 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, u16 ? v0 : v4, 16);
+    const float a1 = (u16 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, u16 ? v1 : v5, 16);
+    const float a2 = (u16 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, u16 ? v2 : v6, 16);
+    const float a3 = (u16 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, u16 ? v3 : v7, 16);
+    const float b0 = (u8 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, u8 ? a0 : a2, 8);
+    const float b1 = (u8 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, u8 ? a1 : a3, 8);
+    float c0 = (u4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, u4 ? b0 : b1, 4);
+    c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+    c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
+    return c0;
+}
+__device__ __forceinline__ void colsum16(const float (&v)[TC_W], float (&acc)[2]) {
+    acc[0] += colsum8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    acc[1] += colsum8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
 }
 
-// GroupNorm statistics of a row in registers: z -> zhat in place, rstd per group
-__device__ __forceinline__ void tc_gn_normalize(float (&z)[HID], float (&rstd)[GROUPS]) {
+// GroupNorm on the thread's two groups: z -> zhat in place, rstd per group
+__device__ __forceinline__ void gn_normalize16(float (&z)[TC_W], float (&rstd)[2]) {
 #pragma unroll
-    for (int g = 0; g < GROUPS; ++g) {
+    for (int g = 0; g < 2; ++g) {
         float m = 0.f;
 #pragma unroll
         for (int i = 0; i < GSIZE; ++i) m += z[g * GSIZE + i];
@@ -89,16 +91,16 @@ __device__ __forceinline__ void tc_gn_normalize(float (&z)[HID], float (&rstd)[G
         float v = 0.f;
 #pragma unroll
         for (int i = 0; i < GSIZE; ++i) { const float d = z[g * GSIZE + i] - m; v = fmaf(d, d, v); }
-        const float r = 1.0f / sqrtf(v * (1.0f / GSIZE) + GN_EPS);
+        const float r = rsqrtf(v * (1.0f / GSIZE) + GN_EPS);
         rstd[g] = r;
 #pragma unroll
         for (int i = 0; i < GSIZE; ++i) z[g * GSIZE + i] = (z[g * GSIZE + i] - m) * r;
     }
 }
 // dy -> dz in place: d = dy * gamma, dz = rstd * (d - mean(d) - zhat * mean(d * zhat)) per group
-__device__ __forceinline__ void tc_gn_backward(float (&d)[HID], const float (&zhat)[HID], const float (&rstd)[GROUPS], const float *gamma) {
+__device__ __forceinline__ void gn_backward16(float (&d)[TC_W], const float (&zhat)[TC_W], const float (&rstd)[2], const float (&gamma)[TC_W]) {
 #pragma unroll
-    for (int g = 0; g < GROUPS; ++g) {
+    for (int g = 0; g < 2; ++g) {
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
         for (int i = 0; i < GSIZE; ++i) {
@@ -115,6 +117,13 @@ __device__ __forceinline__ void tc_gn_backward(float (&d)[HID], const float (&zh
         }
     }
 }
+__device__ __forceinline__ void load16(const float *src, float (&v)[TC_W]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 t = reinterpret_cast<const float4 *>(src)[i];
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
 
 __device__ __forceinline__ void tc_sync_for_mma() {
     fence_async_smem();
@@ -122,62 +131,54 @@ __device__ __forceinline__ void tc_sync_for_mma() {
     __syncthreads();
 }
 
-// ---- MMA issue (one thread) ---------------------------------------------------------------------------------------
-struct TcAddr {
-    uint32_t W, F, DZ, X, tmem;
+// ---- MMA issue: all lanes of warp 0 call these (warp-uniform), one elected lane issues --------------------------------
+struct TcDesc {          // base descriptors, K-major and MN-major views, built once per kernel
+    uint64_t F_k, W_k, DZ_k, W_mn, DZ_mn, F_mn, X_mn;
+    uint32_t tmem;
 };
-// six-term product of two bf16x3 operands: (piece of A, piece of B)
-__device__ __constant__ const int TERM_A[6] = {0, 0, 1, 1, 0, 2};
-__device__ __constant__ const int TERM_B[6] = {0, 1, 0, 1, 2, 0};
+__device__ __forceinline__ uint64_t dadd(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-__device__ __forceinline__ void issue_forward(const TcAddr &a) {
+__device__ __forceinline__ void issue_forward(const TcDesc &D) {
     constexpr uint32_t id = idesc_bf16(128, 128, 0, 0);
-#pragma unroll 1
+    constexpr int TA[6] = {0, 0, 1, 1, 0, 2}, TB[6] = {0, 1, 0, 1, 2, 0};
+#pragma unroll
     for (int t = 0; t < 6; ++t)
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-            mma_bf16_ss(a.tmem + TM_Z, smem_desc(a.F + TERM_A[t] * PIECE + s * 2 * CHUNK, CHUNK, 128),
-                        smem_desc(a.W + TERM_B[t] * PIECE + s * 2 * CHUNK, CHUNK, 128), id, (t | s) != 0);
+            mma_bf16_ss(D.tmem + TM_Z, dadd(D.F_k, TA[t] * PIECE + s * 2 * CHUNK), dadd(D.W_k, TB[t] * PIECE + s * 2 * CHUNK), id, (t | s) != 0);
 }
-__device__ __forceinline__ void issue_head_backward(const TcAddr &a, int h, bool first_tile) {
+__device__ __forceinline__ void issue_head_backward(const TcDesc &D, int h, bool first_tile) {
     constexpr uint32_t id_d = idesc_bf16(128, 64, 0, 1), id_w = idesc_bf16(128, 64, 1, 1);
-    // dgrad: DF (+)= DZ_h . W1_h   (B: MN-major view, MN = k groups CHUNK apart, K = j groups 128 B apart, head h at + h*64*16)
-#pragma unroll 1
+    constexpr int TA[6] = {0, 0, 1, 1, 0, 2}, TB[6] = {0, 1, 0, 1, 2, 0};
+    // dgrad: DF (+)= DZ_h . W1_h   (B: MN-major view of W1, head h starts 64 rows = 1024 B in; 16 j's per step = 256 B)
+    const uint64_t wh = dadd(D.W_mn, h * 64 * 16);
+#pragma unroll
     for (int t = 0; t < 6; ++t)
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-            mma_bf16_ss(a.tmem + TM_DF, smem_desc(a.DZ + TERM_A[t] * PIECE + s * 2 * CHUNK, CHUNK, 128),
-                        smem_desc(a.W + TERM_B[t] * PIECE + h * 64 * 16 + s * 256, 128, CHUNK), id_d, (h | t | s) != 0);
+            mma_bf16_ss(D.tmem + TM_DF, dadd(D.DZ_k, TA[t] * PIECE + s * 2 * CHUNK), dadd(wh, TB[t] * PIECE + s * 256), id_d, (h | t | s) != 0);
     // wgrad: DW_h[(piece window, j)][k] += sum_r DZ[r][.] F[r][k]; windows [p0|p1] x f0, f1, f2 and [p2|0] x f0
-#pragma unroll 1
+    const uint32_t dw = D.tmem + TM_DW + 64 * h;
+#pragma unroll
     for (int t = 0; t < 4; ++t) {
         const uint32_t win = (t == 3) ? 2 * PIECE : 0, fp = (t == 3) ? 0 : t * PIECE;
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
-            mma_bf16_ss(a.tmem + TM_DW + 64 * h, smem_desc(a.DZ + win + s * 256, 128, CHUNK), smem_desc(a.F + fp + s * 256, 128, CHUNK), id_w,
-                        !(first_tile && t == 0 && s == 0));
+        for (int s = 0; s < 8; ++s) mma_bf16_ss(dw, dadd(D.DZ_mn, win + s * 256), dadd(D.F_mn, fp + s * 256), id_w, !(first_tile && t == 0 && s == 0));
     }
 }
-__device__ __forceinline__ void issue_trunk_wgrad(const TcAddr &a, bool first_tile) {
+__device__ __forceinline__ void issue_trunk_wgrad(const TcDesc &D, bool first_tile) {
     constexpr uint32_t id = idesc_bf16(128, 16, 1, 1);
-#pragma unroll 1
+#pragma unroll
     for (int t = 0; t < 4; ++t) {
         const uint32_t win = (t == 3) ? 2 * PIECE : 0, xp = (t == 3) ? 0 : t * XPIECE;
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-            mma_bf16_ss(a.tmem + TM_DW0, smem_desc(a.DZ + win + s * 256, 128, CHUNK), smem_desc(a.X + xp + s * 256, 128, CHUNK), id,
-                        !(first_tile && t == 0 && s == 0));
+            mma_bf16_ss(D.tmem + TM_DW0, dadd(D.DZ_mn, win + s * 256), dadd(D.X_mn, xp + s * 256), id, !(first_tile && t == 0 && s == 0));
     }
 }
 
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[HID]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float t[16];
-        tmem_ld16(taddr + 16 * c, t);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 * c + i] = t[i];
-    }
+__device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[TC_W]) {
+    tmem_ld16(taddr, v);
     tmem_ld_wait();
 }
 
@@ -192,48 +193,45 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     __shared__ uint64_t bars[4];          // forward done, actor backward done, critic backward done, trunk wgrad done
     __shared__ uint32_t tmem_slot;
     __shared__ double red[32];
+    __shared__ float b2s[4][2][TC_MAX_A];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rq = warp & 3, q = warp >> 2;      // row quarter (= tensor-memory lane quarter), feature quarter
+    const int r = rq * 32 + lane, j0 = TC_W * q; // row of the tile, first feature of this thread
     const int O = L.O, A = L.A;
 
-    // ---- carve shared memory
-    TcSmem S;
-    {
-        unsigned char *p = smem_raw;
-        S.W = p; p += 3 * PIECE;
-        S.F = p; p += 3 * PIECE;
-        S.DZ = p; p += 4 * PIECE;
-        S.X = p; p += 3 * XPIECE;
-        float *f = reinterpret_cast<float *>(p);
-        S.w0t = f; f += O * HID;
-        S.g0w = f; f += HID;
-        S.g0b = f; f += HID;
-        for (int h = 0; h < 2; ++h) {
-            S.gw[h] = f; f += HID;
-            S.gb[h] = f; f += HID;
-            S.w2[h] = f; f += L.head[h].out * HID;
-            S.b2[h] = f; f += round4(L.head[h].out);
-        }
-        S.red = f;
-    }
-    // ---- stage parameters: fp32 small ones, W1 of both heads as bf16x3 in the operand layout (row n = h*64 + j)
-    stage_transposed(S.w0t, params + L.w0, HID, O);
-    stage_copy(S.g0w, params + L.g0w, HID);
-    stage_copy(S.g0b, params + L.g0b, HID);
+    // ---- carve shared memory (all pointers derive from smem_raw so they stay in the shared state space)
+    unsigned char *sW = smem_raw, *sF = sW + 3 * PIECE, *sDZ = sF + 3 * PIECE, *sX = sDZ + 4 * PIECE;
+    float *sSmall = reinterpret_cast<float *>(sX + 3 * XPIECE);
+    float *s_w0t = sSmall, *s_g0w = s_w0t + O * HID, *s_g0b = s_g0w + HID;
+    float *s_head0 = s_g0b + HID;                                   // per head: gw[64] gb[64] w2[out][64] b2[round4(out)]
+    const int head0_floats = 2 * HID + L.head[0].out * HID + round4(L.head[0].out);
+    float *s_head1 = s_head0 + head0_floats;
+    float *s_po = s_head1 + 2 * HID + L.head[1].out * HID + round4(L.head[1].out);   // [4 q][128 r][NA] partial head outputs
+    float *s_red = s_po + 4 * TC_ROWS * NA;                                            // [4 rq][NQ][64] final combine
+
+    // ---- stage parameters: fp32 small ones; W1 of both heads as bf16x3 in the operand layout (row n = h*64 + j)
+    stage_transposed(s_w0t, params + L.w0, HID, O);
+    stage_copy(s_g0w, params + L.g0w, HID);
+    stage_copy(s_g0b, params + L.g0b, HID);
     for (int h = 0; h < 2; ++h) {
-        stage_copy(S.gw[h], params + L.head[h].gw, HID);
-        stage_copy(S.gb[h], params + L.head[h].gb, HID);
-        stage_copy(S.w2[h], params + L.head[h].w2, L.head[h].out * HID);
-        stage_copy(S.b2[h], params + L.head[h].b2, L.head[h].out);
+        float *sh = h ? s_head1 : s_head0;
+        stage_copy(sh, params + L.head[h].gw, HID);
+        stage_copy(sh + HID, params + L.head[h].gb, HID);
+        stage_copy(sh + 2 * HID, params + L.head[h].w2, L.head[h].out * HID);
+        stage_copy(sh + 2 * HID + L.head[h].out * HID, params + L.head[h].b2, L.head[h].out);
     }
     {
-        const float *wrow = params + L.head[tid >> 6].w1 + (tid & 63) * HID;   // thread n stages row n of the stacked [128][64] W1
-        float v[HID];
+        // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
+        const float *wrow = params + L.head[r >> 6].w1 + (r & 63) * HID + j0;
+        float v[TC_W];
 #pragma unroll
-        for (int k = 0; k < HID; ++k) v[k] = __ldg(wrow + k);
-        store_row_pieces(S.W, tid, v);
-        // zero slot behind the three DZ pieces, and the X pieces (columns >= O stay zero for the whole kernel)
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(S.DZ + 3 * PIECE + c * CHUNK + tid * 16) = make_uint4(0, 0, 0, 0);
-        for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(S.X + c * CHUNK + tid * 16) = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < TC_W; ++k) v[k] = __ldg(wrow + k);
+        store_pieces16(sW, r, q, v);
+        // zero slot behind the three DZ pieces; X pieces (columns >= O stay zero for the whole kernel)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) *reinterpret_cast<uint4 *>(sDZ + 3 * PIECE + (2 * q + c) * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+        if (q == 0)
+            for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
@@ -242,62 +240,86 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     if (warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
     tc_sync_for_mma();
     fence_after_sync();
-    TcAddr addr{smem_u32(S.W), smem_u32(S.F), smem_u32(S.DZ), smem_u32(S.X), tmem_slot};
-    const uint32_t lane_base = addr.tmem + ((uint32_t)(warp * 32) << 16);
+    TcDesc D;
+    D.tmem = tmem_slot;
+    D.F_k = smem_desc(smem_u32(sF), CHUNK, 128);
+    D.W_k = smem_desc(smem_u32(sW), CHUNK, 128);
+    D.DZ_k = smem_desc(smem_u32(sDZ), CHUNK, 128);
+    D.W_mn = smem_desc(smem_u32(sW), 128, CHUNK);
+    D.DZ_mn = smem_desc(smem_u32(sDZ), 128, CHUNK);
+    D.F_mn = smem_desc(smem_u32(sF), 128, CHUNK);
+    D.X_mn = smem_desc(smem_u32(sX), 128, CHUNK);
+    const uint32_t lane_base = D.tmem + ((uint32_t)(rq * 32) << 16);
     bool mma_ok = true;
 
-    // per-warp column-sum accumulators, features 2*lane and 2*lane+1: trunk (dgamma, dbeta), head h (dgamma, dbeta, dW2[a])
+    // per-warp column-sum accumulators for this thread's two groups (feature f(lane) of each)
     float q_g0[2] = {0.f, 0.f}, q_b0[2] = {0.f, 0.f};
     float q_g[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, q_b[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    float q_w2[2][NA][2];
-    float q_b2[2][NA];
+    float q_w2[2][NA][2], q_b2[2][NA];
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int a = 0; a < NA; ++a) { q_w2[h][a][0] = q_w2[h][a][1] = 0.f; q_b2[h][a] = 0.f; }
     double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
 
-    const int64_t ntiles = (b + TC_THREADS - 1) / TC_THREADS;
+    const int64_t ntiles = (b + TC_ROWS - 1) / TC_ROWS;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t parity = it & 1;
-        const int64_t row = tile * TC_THREADS + tid;
+        const int64_t row = tile * TC_ROWS + r;
         const bool live = row < b;
-        const float *xrow = states + (live ? row : 0) * O;   // dead rows read row 0 and are masked below
+        const float *xrow = states + (live ? row : 0) * O;   // dead rows read row 0 and are masked
         const float xmask = live ? 1.f : 0.f;
 
         // ================= trunk forward (CUDA cores): z0 = W0 x, GroupNorm, SiLU -> F pieces, X pieces
+        float zh0[TC_W], rs0[2];
         {
-            float z[HID], rstd[GROUPS];
 #pragma unroll
-            for (int j = 0; j < HID; ++j) z[j] = 0.f;
-            for (int i = 0; i < O; ++i) axpy64(xmask * __ldg(xrow + i), S.w0t + i * HID, z);
-            tc_gn_normalize(z, rstd);
+            for (int j = 0; j < TC_W; ++j) zh0[j] = 0.f;
+            for (int i = 0; i < O; ++i) {
+                const float xi = xmask * __ldg(xrow + i);
+                float w[TC_W];
+                load16(s_w0t + i * HID + j0, w);
 #pragma unroll
-            for (int j = 0; j < HID; ++j) z[j] = silu(fmaf(z[j], S.g0w[j], S.g0b[j]));
+                for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(xi, w[j], zh0[j]);
+            }
+            gn_normalize16(zh0, rs0);
+            float f[TC_W], g0w[TC_W], g0b[TC_W];
+            load16(s_g0w + j0, g0w);
+            load16(s_g0b + j0, g0b);
+#pragma unroll
+            for (int j = 0; j < TC_W; ++j) {
+                const float y = fmaf(zh0[j], g0w[j], g0b[j]);
+                f[j] = y * fast_sigmoid(y);
+            }
             // the previous tile's trunk-wgrad MMAs read X and DZ; its head MMAs (already waited for) read F
             if (it > 0) mma_ok &= mbar_wait(&bars[3], parity ^ 1);
-            store_row_pieces(S.F, tid, z);
+            store_pieces16(sF, r, q, f);
+            if (q == 0) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t q0[4], q1[4], q2[4];
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t q0[4], q1[4], q2[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = 8 * c + 2 * i;
-                    const float xa = e < O ? xmask * __ldg(xrow + e) : 0.f, xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f;
-                    split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = 8 * c + 2 * i;
+                        const float xa = e < O ? xmask * __ldg(xrow + e) : 0.f, xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f;
+                        split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
+                    }
+                    unsigned char *p = sX + c * CHUNK + r * 16;
+                    *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+                    *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+                    *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
                 }
-                unsigned char *p = S.X + c * CHUNK + tid * 16;
-                *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
-                *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-                *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
             }
         }
         tc_sync_for_mma();
-        if (tid == 0) {
+        if (warp == 0) {
             fence_after_sync();
-            issue_forward(addr);
-            mma_commit(&bars[0]);
+            if (elect_one()) {
+                issue_forward(D);
+                mma_commit(&bars[0]);
+            }
+            __syncwarp();
         }
         const float adv_i = live ? adv[row] : 0.f, old_i = live ? old_logp[row] : 0.f;
         const float ret_i = live ? returns[row] : 0.f;
@@ -306,27 +328,39 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         fence_after_sync();
 
         // ================= heads: forward epilogue, loss, backward epilogue -> DZ pieces, tensor-core dgrad + wgrad
-#pragma unroll 1
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int nout = L.head[h].out;
-            const float *gw = S.gw[h], *gb = S.gb[h], *w2 = S.w2[h];
-            float zhat[HID], rstd[GROUPS], sg[HID];
-            tmem_ld64(lane_base + TM_Z + 64 * h, zhat);
-            tc_gn_normalize(zhat, rstd);
-            float out[NA];
+            const float *sh = h ? s_head1 : s_head0;
+            const float *w2 = sh + 2 * HID;
+            float gw[TC_W], gb[TC_W];
+            load16(sh + j0, gw);
+            load16(sh + HID + j0, gb);
+            float zhat[TC_W], rstd[2], sg[TC_W];
+            tmem_ld16w(lane_base + TM_Z + 64 * h + j0, zhat);
+            gn_normalize16(zhat, rstd);
+            float po[NA];
 #pragma unroll
-            for (int a = 0; a < NA; ++a) out[a] = (a < nout) ? S.b2[h][a] : 0.f;
+            for (int a = 0; a < NA; ++a) po[a] = 0.f;
 #pragma unroll
-            for (int j = 0; j < HID; ++j) {
+            for (int j = 0; j < TC_W; ++j) {
                 const float y = fmaf(zhat[j], gw[j], gb[j]);
-                const float s = 1.0f / (1.0f + expf(-y));
-                sg[j] = s;
-                const float hj = y * s;
+                sg[j] = fast_sigmoid(y);
+                const float hj = y * sg[j];
 #pragma unroll
                 for (int a = 0; a < NA; ++a)
-                    if (a < nout) out[a] = fmaf(hj, w2[a * HID + j], out[a]);
+                    if (a < nout) po[a] = fmaf(hj, w2[a * HID + j0 + j], po[a]);
             }
-            // ---- loss and output gradients
+#pragma unroll
+            for (int a = 0; a < NA; ++a) s_po[(q * TC_ROWS + r) * NA + a] = po[a];
+            __syncthreads();
+            float out[NA];
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                out[a] = (a < nout) ? w2[nout * HID + a] + ((s_po[(0 * TC_ROWS + r) * NA + a] + s_po[(1 * TC_ROWS + r) * NA + a]) +
+                                                          (s_po[(2 * TC_ROWS + r) * NA + a] + s_po[(3 * TC_ROWS + r) * NA + a]))
+                                    : 0.f;
+            // ---- loss and output gradients (the four threads of a row compute them redundantly; q == 0 keeps the sums)
             float dout[NA];
 #pragma unroll
             for (int a = 0; a < NA; ++a) dout[a] = 0.f;
@@ -353,105 +387,98 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     }
                     const float logp = logf(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
                     const float dl = logp - old_i;
-                    const float r = expf(fminf(fmaxf(dl, -20.f), 20.f));
-                    const float s1 = r * adv_i;
-                    const float s2 = fminf(fmaxf(r, 1.0f - clip), 1.0f + clip) * adv_i;
+                    const float rr = expf(fminf(fmaxf(dl, -20.f), 20.f));
+                    const float s1 = rr * adv_i;
+                    const float s2 = fminf(fmaxf(rr, 1.0f - clip), 1.0f + clip) * adv_i;
                     const float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // torch.min splits ties evenly
-                    const float in_clip = (r >= 1.0f - clip && r <= 1.0f + clip) ? 1.f : 0.f;
+                    const float in_clip = (rr >= 1.0f - clip && rr <= 1.0f + clip) ? 1.f : 0.f;
                     const float in20 = (dl >= -20.f && dl <= 20.f) ? 1.f : 0.f;
-                    float dlogp = -inv_count * adv_i * (g1 + (1.f - g1) * in_clip) * r * in20;
+                    float dlogp = -inv_count * adv_i * (g1 + (1.f - g1) * in_clip) * rr * in20;
                     if (!(pa >= F32_EPS && pa <= 1.0f - F32_EPS)) dlogp = 0.f;   // clamp in probs_to_logits blocks the gradient
 #pragma unroll
                     for (int a = 0; a < NA; ++a)
                         if (a < A) dout[a] = dlogp * ((a == act ? 1.f : 0.f) - p[a]);
-                    l_pol += -fminf(s1, s2);
-                    l_ent += ent;
+                    if (q == 0) { l_pol += -fminf(s1, s2); l_ent += ent; }
                 }
             } else if (live) {
                 const float dv = out[0] - ret_i, ad = fabsf(dv);
-                l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
+                if (q == 0) l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
                 dout[0] = 0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f));
             }
             // ---- output-layer gradients: dW2[a][j] = sum_r dout[a] h_j, db2[a] = sum_r dout[a]
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
                 if (a < nout) {
-                    float t[HID];
+                    float t[TC_W];
 #pragma unroll
-                    for (int j = 0; j < HID; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
-                    float s0, s1;
-                    warp_colsum64(t, s0, s1);
-                    q_w2[h][a][0] += s0; q_w2[h][a][1] += s1;
-                    q_b2[h][a] += warp_sum(dout[a]);
+                    for (int j = 0; j < TC_W; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
+                    colsum16(t, q_w2[h][a]);
+                    if (q == 0) q_b2[h][a] += warp_sum(dout[a]);
                 }
             }
-            // ---- dy (in place of sg), GroupNorm-affine gradients
+            // ---- dy (in place of sg), GroupNorm-affine gradients, GroupNorm backward -> dz
 #pragma unroll
-            for (int j = 0; j < HID; ++j) {
+            for (int j = 0; j < TC_W; ++j) {
                 float dh = 0.f;
 #pragma unroll
                 for (int a = 0; a < NA; ++a)
-                    if (a < nout) dh = fmaf(dout[a], w2[a * HID + j], dh);
+                    if (a < nout) dh = fmaf(dout[a], w2[a * HID + j0 + j], dh);
                 const float y = fmaf(zhat[j], gw[j], gb[j]);
                 sg[j] = dh * sg[j] * fmaf(y, 1.0f - sg[j], 1.0f);
             }
             {
-                float t[HID], s0, s1;
+                float t[TC_W];
 #pragma unroll
-                for (int j = 0; j < HID; ++j) t[j] = sg[j] * zhat[j];
-                warp_colsum64(t, s0, s1);
-                q_g[h][0] += s0; q_g[h][1] += s1;
-#pragma unroll
-                for (int j = 0; j < HID; ++j) t[j] = sg[j];
-                warp_colsum64(t, s0, s1);
-                q_b[h][0] += s0; q_b[h][1] += s1;
+                for (int j = 0; j < TC_W; ++j) t[j] = sg[j] * zhat[j];
+                colsum16(t, q_g[h]);
+                colsum16(sg, q_b[h]);
             }
-            tc_gn_backward(sg, zhat, rstd, gw);   // sg now holds dz
+            gn_backward16(sg, zhat, rstd, gw);   // sg now holds dz
             // the actor's MMAs read DZ: they must have completed before the critic overwrites it
             if (h == 1) mma_ok &= mbar_wait(&bars[1], parity);
-            store_row_pieces(S.DZ, tid, sg);
+            store_pieces16(sDZ, r, q, sg);
             tc_sync_for_mma();
-            if (tid == 0) {
+            if (warp == 0) {
                 fence_after_sync();
-                issue_head_backward(addr, h, it == 0);
-                mma_commit(&bars[1 + h]);
+                if (elect_one()) {
+                    issue_head_backward(D, h, it == 0);
+                    mma_commit(&bars[1 + h]);
+                }
+                __syncwarp();
             }
         }
 
         // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
         {
-            float zhat[HID], rstd[GROUPS], df[HID];
-#pragma unroll
-            for (int j = 0; j < HID; ++j) zhat[j] = 0.f;
-            for (int i = 0; i < O; ++i) axpy64(xmask * __ldg(xrow + i), S.w0t + i * HID, zhat);
-            tc_gn_normalize(zhat, rstd);
+            float df[TC_W], g0w[TC_W], g0b[TC_W];
+            load16(s_g0w + j0, g0w);
+            load16(s_g0b + j0, g0b);
             mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final; DZ free again
             fence_after_sync();
-            tmem_ld64(lane_base + TM_DF, df);
+            tmem_ld16w(lane_base + TM_DF + j0, df);
 #pragma unroll
-            for (int j = 0; j < HID; ++j) {
-                const float y = fmaf(zhat[j], S.g0w[j], S.g0b[j]);
-                const float s = 1.0f / (1.0f + expf(-y));
+            for (int j = 0; j < TC_W; ++j) {
+                const float y = fmaf(zh0[j], g0w[j], g0b[j]);
+                const float s = fast_sigmoid(y);
                 df[j] = df[j] * s * fmaf(y, 1.0f - s, 1.0f);
             }
             {
-                float t[HID], s0, s1;
+                float t[TC_W];
 #pragma unroll
-                for (int j = 0; j < HID; ++j) t[j] = df[j] * zhat[j];
-                warp_colsum64(t, s0, s1);
-                q_g0[0] += s0; q_g0[1] += s1;
-#pragma unroll
-                for (int j = 0; j < HID; ++j) t[j] = df[j];
-                warp_colsum64(t, s0, s1);
-                q_b0[0] += s0; q_b0[1] += s1;
+                for (int j = 0; j < TC_W; ++j) t[j] = df[j] * zh0[j];
+                colsum16(t, q_g0);
+                colsum16(df, q_b0);
             }
-            tc_gn_backward(df, zhat, rstd, S.g0w);
-            store_row_pieces(S.DZ, tid, df);
+            gn_backward16(df, zh0, rs0, g0w);
+            store_pieces16(sDZ, r, q, df);
             tc_sync_for_mma();
-            if (tid == 0) {
+            if (warp == 0) {
                 fence_after_sync();
-                issue_trunk_wgrad(addr, it == 0);
-                mma_commit(&bars[3]);
+                if (elect_one()) {
+                    issue_trunk_wgrad(D, it == 0);
+                    mma_commit(&bars[3]);
+                }
+                __syncwarp();
             }
         }
     }
@@ -461,57 +488,64 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     float *part = partials + (size_t)blockIdx.x * P;
     if (it > 0) mma_ok &= mbar_wait(&bars[3], (it - 1) & 1);
     fence_after_sync();
-    float *scratch = reinterpret_cast<float *>(S.F);   // 64 x 64 fp32 = 16 KB, free now
+    float *scratch = reinterpret_cast<float *>(sF);   // [64][65] + [64][17] fp32 inside the 48 KB F region, free now
+    // DW_h: lanes 0..63 hold the first piece window's products, lanes 64..127 the second's; thread (r, q) reads 16 columns
     for (int h = 0; h < 2; ++h) {
-        float v[HID];
-        tmem_ld64(lane_base + TM_DW + 64 * h, v);     // lanes 0..63: first piece of the window, lanes 64..127: second
+        float v[TC_W];
+        tmem_ld16w(lane_base + TM_DW + 64 * h + j0, v);
         __syncthreads();
-        if (tid >= 64) {
+        if (r >= 64) {
 #pragma unroll
-            for (int k = 0; k < HID; ++k) scratch[(tid - 64) * (HID + 1) + k] = v[k];
+            for (int k = 0; k < TC_W; ++k) scratch[(r - 64) * (HID + 1) + j0 + k] = v[k];
         }
         __syncthreads();
-        if (tid < 64) {
-            float *dst = part + L.head[h].w1 + tid * HID;
+        if (r < 64) {
+            float *dst = part + L.head[h].w1 + r * HID + j0;
 #pragma unroll
-            for (int k = 0; k < HID; ++k) dst[k] = (it > 0) ? v[k] + scratch[tid * (HID + 1) + k] : 0.f;
+            for (int k = 0; k < TC_W; ++k) dst[k] = (it > 0) ? v[k] + scratch[r * (HID + 1) + j0 + k] : 0.f;
         }
     }
     {
-        float v[16];
-        tmem_ld16(lane_base + TM_DW0, v);
-        tmem_ld_wait();
-        __syncthreads();
-        if (tid >= 64) {
+        float v[TC_W];
+        tmem_ld16w(lane_base + TM_DW0, v);
+        if (q == 0 && r >= 64) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scratch[(tid - 64) * 17 + i] = v[i];
+            for (int i = 0; i < TC_W; ++i) scratch[64 * (HID + 1) + (r - 64) * 17 + i] = v[i];
         }
         __syncthreads();
-        if (tid < 64) {
+        if (q == 0 && r < 64) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < O) part[L.w0 + tid * O + i] = (it > 0) ? v[i] + scratch[tid * 17 + i] : 0.f;
+            for (int i = 0; i < TC_W; ++i)
+                if (i < O) part[L.w0 + r * O + i] = (it > 0) ? v[i] + scratch[64 * (HID + 1) + r * 17 + i] : 0.f;
         }
     }
-    // column-sum accumulators: combine the four warps through shared memory, features 2*lane, 2*lane+1
+    // column-sum accumulators: lanes with (lane & 3) == 0 publish feature 16q + 8g + f(lane); combine the four row quarters
     {
         __syncthreads();
         const int NQ = tc_num_q(L);
-        float *r4 = S.red + (size_t)warp * NQ * HID;
-        int q = 0;
-        auto put = [&](const float (&s)[2]) { r4[q * HID + 2 * lane] = s[0]; r4[q * HID + 2 * lane + 1] = s[1]; ++q; };
-        put(q_g0); put(q_b0);
-        for (int h = 0; h < 2; ++h) {
-            put(q_g[h]); put(q_b[h]);
+        float *r4 = s_red + (size_t)rq * NQ * HID;
+        const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0) {
+            int qq = 0;
+            auto put = [&](const float (&s)[2]) { r4[qq * HID + j0 + f] = s[0]; r4[qq * HID + j0 + 8 + f] = s[1]; ++qq; };
+            put(q_g0); put(q_b0);
 #pragma unroll
-            for (int a = 0; a < NA; ++a)
-                if (a < L.head[h].out) put(q_w2[h][a]);
+            for (int h = 0; h < 2; ++h) {
+                put(q_g[h]); put(q_b[h]);
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+                    if (a < L.head[h].out) put(q_w2[h][a]);
+            }
         }
+        if (q == 0 && lane == 0)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int a = 0; a < NA; ++a) b2s[rq][h][a] = q_b2[h][a];
         __syncthreads();
-        // destination offsets of the NQ vectors in the flat gradient
         for (int idx = tid; idx < NQ * HID; idx += TC_THREADS) {
             const int qq = idx / HID, j = idx - qq * HID;
-            const float s = (S.red[(0 * NQ + qq) * HID + j] + S.red[(1 * NQ + qq) * HID + j]) + (S.red[(2 * NQ + qq) * HID + j] + S.red[(3 * NQ + qq) * HID + j]);
+            const float s = (s_red[(0 * NQ + qq) * HID + j] + s_red[(1 * NQ + qq) * HID + j]) + (s_red[(2 * NQ + qq) * HID + j] + s_red[(3 * NQ + qq) * HID + j]);
             int off;
             if (qq == 0) off = L.g0w;
             else if (qq == 1) off = L.g0b;
@@ -522,13 +556,6 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             }
             part[off + j] = s;
         }
-        // db2: every lane of a warp holds the warp total; combine warps
-        __shared__ float b2s[4][2][NA];
-        if (lane == 0)
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int a = 0; a < NA; ++a) b2s[warp][h][a] = q_b2[h][a];
-        __syncthreads();
         if (tid < 2 * NA) {
             const int h = tid / NA, a = tid % NA;
             if (a < L.head[h].out) part[L.head[h].b2 + a] = (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]);
@@ -542,12 +569,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         loss_partials[blockIdx.x * 4 + 1] = bv;
         loss_partials[blockIdx.x * 4 + 2] = be;
         loss_partials[blockIdx.x * 4 + 3] = 0.0;
-        if (!mma_ok) atomicExch(status, 1);
     }
-    if (!mma_ok && lane == 0 && tid != 0) atomicExch(status, 1);
+    if (!mma_ok && lane == 0) atomicExch(status, 1);
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(addr.tmem, TM_COLS);
+    if (warp == 0) tmem_dealloc(D.tmem, TM_COLS);
 }
 
 // grad[i] = sum over blocks of partials[b][i], fixed order (bit-reproducible); loss_out += block loss partials
@@ -571,7 +597,7 @@ static int tc_grid(int64_t b) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t ntiles = (b + TC_THREADS - 1) / TC_THREADS;
+    const int64_t ntiles = (b + TC_ROWS - 1) / TC_ROWS;
     return (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
 }
 
@@ -588,7 +614,7 @@ int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim) {
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(batch);
-    return (size_t)grid * L.total + (size_t)grid * 8 + 16;
+    return 4 + (size_t)grid * L.total + (size_t)grid * 8 + 16;
 }
 
 int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
@@ -600,33 +626,32 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
                 TC_MAX_A, is_continuous, obs_dim, action_dim);
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(b);
-    PRL_REQUIRE(ws_floats >= (size_t)grid * L.total + (size_t)grid * 8 + 16, "prl_ppo_grad_tc: workspace too small");
-    const size_t smem = tc_smem_bytes(L);
+    PRL_REQUIRE(ws_floats >= 4 + (size_t)grid * L.total + (size_t)grid * 8 + 16, "prl_ppo_grad_tc: workspace too small");
+    const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
+    const size_t smem = tc_smem_bytes(L, NA);
     PRL_REQUIRE(smem <= 227 * 1024, "prl_ppo_grad_tc: needs %zu B shared memory (> 227 KB)", smem);
     cudaStream_t st = (cudaStream_t)stream;
-    float *partials = ws;
-    double *loss_partials = reinterpret_cast<double *>(ws + (((size_t)grid * L.total + 1) & ~(size_t)1));
-    int *status = reinterpret_cast<int *>(loss_partials + (size_t)grid * 4);
-    PRL_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    // ws[0] = sticky status word (the caller zeroes the workspace once), then the per-block partial gradients and losses
+    int *status = reinterpret_cast<int *>(ws);
+    float *partials = ws + 4;
+    double *loss_partials = reinterpret_cast<double *>(partials + (((size_t)grid * L.total + 1) & ~(size_t)1));
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, TC_THREADS, smem, st>>>(params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials,
                                              loss_partials, status);
         return PRL_OK;
     };
-    const int rc = action_dim <= 2 ? launch(k_ppo_grad_tc<2>) : action_dim <= 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
+    const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
     if (rc != PRL_OK) return rc;
     k_reduce_partials_tc<<<cdiv(L.total, 256), 256, 0, st>>>(partials, grid, L.total, grad, loss_partials, loss_out, (double)b);
     return check_launch("k_ppo_grad_tc");
 }
 
-/* 0 = every tensor-core phase completed; 1 = an mbarrier wait timed out (results invalid).  Host-synchronising. */
-int prl_ppo_grad_tc_status(const float *ws, int is_continuous, int obs_dim, int action_dim, int64_t batch, int *status_host, void *stream) {
+/* ws[0]: 0 = every tensor-core phase of every call since the workspace was zeroed completed; 1 = an mbarrier wait timed
+ * out (results invalid).  Host-synchronising. */
+int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream) {
     PRL_REQUIRE(ws && status_host, "prl_ppo_grad_tc_status: bad arguments");
-    const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    const int grid = tc_grid(batch);
-    const double *loss_partials = reinterpret_cast<const double *>(ws + (((size_t)grid * L.total + 1) & ~(size_t)1));
-    PRL_CUDA(cudaMemcpyAsync(status_host, loss_partials + (size_t)grid * 4, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PRL_CUDA(cudaMemcpyAsync(status_host, ws, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return PRL_OK;
 }

@@ -51,7 +51,7 @@ PROTOTYPES = {
     "prl_ppo_grad_tc_supported": (_i32, [_i32, _i32, _i32]),
     "prl_update_tc_ws_floats": (_sz, [_i32, _i32, _i32, _i64]),
     "prl_ppo_grad_tc": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),
-    "prl_ppo_grad_tc_status": (_i32, [_vp, _i32, _i32, _i32, _i64, _vp, _vp]),
+    "prl_ppo_grad_tc_status": (_i32, [_vp, _vp, _vp]),
     "prl_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _vp, _vp]),
     "prl_rnd_intrinsic": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f32, _vp, _vp, _vp]),
     "prl_rnd_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),

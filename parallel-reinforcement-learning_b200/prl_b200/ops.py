@@ -65,11 +65,15 @@ def test_philox(seed, c0, c1, c2, c3):
 def test_umma(mode, A, B, cfg=None):
     n_out = {0: 128, 1: 64, 2: 64, 3: 16}[mode] if cfg is None else cfg[2]
     D = torch.full((128, n_out), float("nan"), dtype=torch.float32, device=_dev())
-    status = torch.zeros(1, dtype=torch.int32, device=_dev())
-    cfg_arr = (C.c_int32 * 13)(*[int(x) for x in cfg]) if cfg is not None else None
+    status = torch.zeros(2, dtype=torch.int32, device=_dev())   # [0] = timed out, [1] = cycles from first issue to completion
+    if cfg is not None:
+        cfg = list(cfg) + [0, 0, 1][len(cfg) - 13:] if len(cfg) < 16 else list(cfg)
+    cfg_arr = (C.c_int32 * 16)(*[int(x) for x in cfg]) if cfg is not None else None
     call("prl_test_umma", -1 if cfg is not None else mode, _ptr(A, torch.float32), _ptr(B, torch.float32), _ptr(D), _ptr(status),
          cfg_arr, _stream())
-    return D, int(status.item())
+    st = status.cpu().numpy()
+    test_umma.last_cycles = int(st[1])
+    return D, int(st[0])
 
 
 # ------------------------------------------------------------------------------------------------ env state
@@ -263,9 +267,9 @@ def ppo_grad_tc(params, is_continuous, O, A, states, actions, old_logp, adv, ret
          _ptr(ws, torch.float32), ws.numel(), _stream())
 
 
-def ppo_grad_tc_status(ws, is_continuous, O, A, batch):
+def ppo_grad_tc_status(ws):
     st = C.c_int(0)
-    call("prl_ppo_grad_tc_status", _ptr(ws, torch.float32), int(is_continuous), O, A, batch, C.byref(st), _stream())
+    call("prl_ppo_grad_tc_status", _ptr(ws, torch.float32), C.byref(st), _stream())
     return st.value
 
 

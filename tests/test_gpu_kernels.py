@@ -353,9 +353,9 @@ def test_tensor_core_ppo_grad_matches_oracle(ops, golden, name, roll):
     for path in ("tc", "fp32"):
         grad = t.full_like(params, float("nan")); loss = t.zeros(4, dtype=t.float64, device="cuda")
         if path == "tc":
-            ws = t.empty(ops.update_tc_ws_floats(cont, O, A, N), device="cuda")
+            ws = t.zeros(ops.update_tc_ws_floats(cont, O, A, N), device="cuda")
             ops.ppo_grad_tc(params, cont, O, A, s, a, dev(old_lp), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
-            assert ops.ppo_grad_tc_status(ws, cont, O, A, N) == 0
+            assert ops.ppo_grad_tc_status(ws) == 0
         else:
             ws = t.empty(ops.update_ws_floats(cont, O, A, N), device="cuda")
             ops.ppo_grad(params, cont, O, A, s, a, dev(old_lp), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
@@ -387,9 +387,9 @@ def test_tensor_core_ppo_grad_large_batch_matches_fp32_kernel(ops, golden):
     for path in ("tc", "fp32"):
         grad = t.full_like(params, float("nan")); loss = t.zeros(4, dtype=t.float64, device="cuda")
         if path == "tc":
-            ws = t.empty(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
+            ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
             ops.ppo_grad_tc(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
-            assert ops.ppo_grad_tc_status(ws, False, O, A, N) == 0
+            assert ops.ppo_grad_tc_status(ws) == 0
         else:
             ws = t.empty(ops.update_ws_floats(False, O, A, N), device="cuda")
             ops.ppo_grad(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)

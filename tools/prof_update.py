@@ -1,0 +1,35 @@
+"""Profiling driver (GPU box): a few launches of the PPO minibatch-gradient kernels on 65 536 CartPole-shaped rows."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "parallel-reinforcement-learning_b200")]
+import numpy as np, torch as t
+from prl_b200 import ops
+
+path = sys.argv[1] if len(sys.argv) > 1 else "tc"
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+O, A = 4, 2
+g = np.load(os.path.join(ROOT, "tests/golden/learn_discrete.npz"))
+rng = np.random.default_rng(0)
+params = t.from_numpy(g["init_flat"]).cuda()
+s = t.from_numpy(rng.uniform(-1, 1, (N, O)).astype(np.float32)).cuda()
+a = t.from_numpy(rng.integers(0, A, (N, 1)).astype(np.float32)).cuda()
+logp, _, _ = ops.policy_evaluate(params, False, O, A, s, a)
+adv = t.randn(N, device="cuda"); ret = t.randn(N, device="cuda")
+grad = t.zeros_like(params); loss = t.zeros(4, dtype=t.float64, device="cuda")
+if path == "tc":
+    ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
+    fn = lambda: ops.ppo_grad_tc(params, False, O, A, s, a, logp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
+else:
+    ws = t.zeros(ops.update_ws_floats(False, O, A, N), device="cuda")
+    fn = lambda: ops.ppo_grad(params, False, O, A, s, a, logp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
+for _ in range(3):
+    fn()
+t.cuda.synchronize()
+e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    fn()
+e1.record(); t.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(f"{path} N={N}: {ms * 1e3:.1f} us per call, {N / ms / 1e3:.1f} M rows/s, {N * 51840 / ms / 1e9:.2f} TFLOP/s algorithmic")
