@@ -41,7 +41,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--horizon", type=int, default=128)
@@ -202,6 +202,7 @@ def run_b200(args):
     ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=1e-3, k_epochs=args.k_epochs, batch_size=1024,
               mini_batch_size=args.mini_batch * world)
     ppo.show_progress = False
+    ppo.use_cuda_graph = True   # one captured epoch replayed k_epochs times (single process; see PPO.learn)
     ppo._seed += rank  # different action noise per shard
     t.manual_seed(1234 + rank)  # different env reset stream per shard
     ap = AsyncPPO(env=prl_b200.make("CartPole-v1", max_episode_steps=T), ppo=ppo, num_envs=E, steps=1)
@@ -253,9 +254,14 @@ def run_b200(args):
     step(True)  # touch the e2e path once
     clocks = ClockSampler(dev.index) if rank == 0 else None
     time.sleep(0.3)
-    n_dev, ms_dev, counts, prof, (w0, w1) = timed(False, args.steps, profile=True)
+    n_dev, ms_dev, counts, _, (w0, w1) = timed(False, args.steps, profile=False)
     clk = clocks.summary(w0, w1) if clocks else None
     n_e2e, ms_e2e, _, _, _ = timed(True, args.steps, profile=False)
+    # kernel attribution: ONE more step of the same workload, launch by launch (no CUDA graph), every entry-point call
+    # bracketed by CUDA events on the launching stream
+    ppo.use_cuda_graph = False
+    n_prof, ms_prof, _, prof, _ = timed(False, 1, profile=True)
+    ppo.use_cuda_graph = True
 
     # per-entry-point device time (CUDA events on the launching stream, this rank)
     per = {}
@@ -263,20 +269,24 @@ def run_b200(args):
         per[name] = {"calls": len(evs), "ms": sum(a.elapsed_time(b) for a, b in evs)}
     pk = peaks()
     roof = None
-    if "prl_ppo_grad" in per:
-        g = per["prl_ppo_grad"]
-        rows_epochs = n_dev / world * args.k_epochs            # sample-epochs this rank pushed through the update kernel
+    gk = "prl_ppo_grad_tc" if "prl_ppo_grad_tc" in per else "prl_ppo_grad"
+    if gk in per:
+        g = per[gk]
+        rows_epochs = n_prof / world * args.k_epochs           # sample-epochs this rank pushed through the update kernel
         tf = rows_epochs * FLOPS_PER_SAMPLE_EPOCH / (g["ms"] * 1e-3) / 1e12
-        roof = {"kernel": "k_ppo_grad (prl_ppo_grad: fused forward + loss + backward, fp32 FMA path)", "bound": "tensor", "achieved": tf,
+        roof = {"kernel": ("k_ppo_grad_tc (prl_ppo_grad_tc: fused forward + loss + backward, tcgen05 bf16x3 MMAs + CUDA-core epilogues)"
+                           if gk == "prl_ppo_grad_tc" else "k_ppo_grad (prl_ppo_grad: fused forward + loss + backward, fp32 FMA path)"),
+                "bound": "tensor", "achieved": tf,
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"], "traffic": None,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
-                "share_of_step": g["ms"] / ms_dev}
+                "share_of_step": g["ms"] / ms_prof,
+                "measured_on": "one launch-by-launch step after the timed region (the timed region replays CUDA graphs)"}
     hbm = {}
-    bytes_per = {"prl_rollout": 102.0, "prl_gae": 16.0, "prl_adv_normalize": 10.0, "prl_buffer_transfer": 56.0 + 4.0 * E * args.steps / max(n_dev / world, 1)}
+    bytes_per = {"prl_rollout": 102.0, "prl_gae": 16.0, "prl_adv_normalize": 10.0, "prl_buffer_transfer": 56.0 + 4.0 * E / max(n_prof / world, 1)}
     for name, b in bytes_per.items():
         if name in per and per[name]["ms"] > 0:
-            gbs = (n_dev / world) * b / (per[name]["ms"] * 1e-3) / 1e9
+            gbs = (n_prof / world) * b / (per[name]["ms"] * 1e-3) / 1e9
             hbm[name] = {"GB/s": gbs, "frac_of_" + pk["source"] + "_hbm": gbs / pk["hbm"], "bytes_per_transition": b, "ms": per[name]["ms"], "calls": per[name]["calls"]}
 
     if rank != 0:

@@ -159,6 +159,12 @@ int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream);
  * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,
                    float lr, float weight_decay, float max_norm, double *grad_norm_out, void *stream);
+/* same with the optimiser clock in device memory: step_counter points to 24 bytes {int64 step, double beta1^step, double
+ * beta2^step} (zero-initialised = step 0); the kernel advances and stores them, so the identical launch can be replayed
+ * (CUDA graphs over the k_epochs x minibatch loop). */
+int prl_adamw_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                       int64_t *step_counter, float lr, float weight_decay, float max_norm, double *grad_norm_out,
+                       void *stream);
 
 /* ---------------------------------------------------------------- RND (PPO/RND.py:71-115) */
 /* compute_intrinsic_reward: out[i] = beta * || pred(s_i) - target(s_i) ||_2 ; add_to != NULL: out = add_to + that */

@@ -144,7 +144,11 @@ class Memory:
         device = buf.lengths.device
         self._upload_host(buf.O, buf.AW, device)
         base = self._dev_count
-        self.reserve(base + int(n_new), buf.O, buf.AW, device)
+        # room for a full rollout (every env running to the time limit) when that is at most 4 GiB, so that the store
+        # is allocated once instead of growing with the episode lengths
+        full = buf.E * buf.T
+        want = base + (full if full * (buf.O + buf.AW + 2) * 4 <= (4 << 30) else int(n_new))
+        self.reserve(max(want, base + int(n_new)), buf.O, buf.AW, device)
         self._scalar_actions = scalar_actions
         buf.transfer(self._dev["states"], self._dev["actions"], self._dev["rewards"], self._dev["dones"], base, self._total)
         self._dev_count = base + int(n_new)

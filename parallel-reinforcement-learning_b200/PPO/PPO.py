@@ -83,8 +83,10 @@ class PPO:
         self.last_losses = None   # device [steps, 4] float64: sums of (policy term, SmoothL1 term, entropy), rows
         self._grad = t.zeros_like(self.policy.flat)
         self._ws = None
+        self._rows = None
         # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies), "fp32" = CUDA-core
         # FMA kernel (csrc/update_ppo.cu; every configuration).  Same math and tolerances, two members of one family.
+        self.use_cuda_graph = False   # capture each epoch of learn() in a CUDA graph (single process, >= 16 optimiser steps)
         self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
 
     # ------------------------------------------------------------------------------------------------ acting
@@ -138,21 +140,33 @@ class PPO:
         mb = int(self.mini_batch_size)
         comm = pdist.active()
 
+        # per-row scratch, allocated once at the store's capacity and reused by every learn() (no allocator traffic)
+        cap = max(self.memory._dev_cap, N)
+        if self._rows is None or self._rows["cap"] < cap:
+            f32 = lambda: t.empty(cap, dtype=t.float32, device=self.device)  # noqa: E731
+            self._rows = dict(cap=cap, logp=f32(), values=f32(), returns=f32(), adv=f32(), rewards=f32(),
+                              gae_ws=t.empty(int(ops._lib.fn("prl_gae_ws_bytes")(cap)), dtype=t.uint8, device=self.device),
+                              ent=t.zeros(1, dtype=t.float64, device=self.device), stats=t.zeros(4, dtype=t.float64, device=self.device))
+        R = self._rows
+
         # old-policy evaluation (PPO.py:134-154): row-independent, so one launch over all N rows
-        old_logp, old_values, _ = ops.policy_evaluate(self.policy_old.flat, cont, O, A, states, actions)
+        old_logp, old_values, _ = ops.policy_evaluate(self.policy_old.flat, cont, O, A, states, actions, entropy_sum=R["ent"],
+                                                      logp=R["logp"][:N], value=R["values"][:N])
 
         if self.use_RND:  # PPO.py:157-178: rewards + intrinsic, THEN one predictor pass over the same chunks
-            rewards = self.rnd.intrinsic_reward_device(states, add_to=rewards)
+            rewards = self.rnd.intrinsic_reward_device(states, add_to=rewards, out=R["rewards"][:N])
             for i in range(0, N, mb):
                 self.rnd.update_pred_chunk(states[i:i + mb])
         self.memory.clear()  # PPO.py:184 (the device rows stay valid until the next transfer)
 
-        returns = ops.gae(rewards, dones, old_values, self.gamma, self.GAE_lambda)  # next_value = V(last stored state)
+        # next_value = V(last stored state), PPO.py:188
+        returns = ops.gae(rewards, dones, old_values, self.gamma, self.GAE_lambda, out=R["returns"][:N], ws=R["gae_ws"])
         # advantages = returns - values; (adv - mean) / (std + 1e-8) over ALL rows of ALL ranks (PPO.py:198-199)
-        _, stats = ops.adv_normalize(returns, old_values, phase=1)
+        stats = R["stats"].zero_()
+        ops.adv_normalize(returns, old_values, stats=stats, phase=1)
         if comm is not None:
             comm.allreduce_(stats)
-        adv, _ = ops.adv_normalize(returns, old_values, stats=stats, phase=2)
+        adv, _ = ops.adv_normalize(returns, old_values, stats=stats, phase=2, out=R["adv"][:N])
 
         # minibatch schedule: sequential chunks of the flat env-major buffer, same order every epoch (PPO.py:202-211).
         # Sharded: global minibatch k = union of every rank's k-th local chunk.
@@ -170,26 +184,56 @@ class PPO:
         if self._ws is None or self._ws.numel() < need:
             self._ws = t.zeros(need, dtype=t.float32, device=self.device)
         steps = self.k_epochs * n_mb
-        self.last_losses = t.zeros(steps, 4, dtype=t.float64, device=self.device)
+
+        def minibatch_step(k, loss_slot):
+            lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
+            if hi > lo:
+                grad_fn(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
+                        returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, loss_slot, self._ws)
+            else:
+                self._grad.zero_()  # this rank has no rows in minibatch k; it still joins the allreduce
+            if comm is not None:
+                comm.allreduce_(self._grad)
+            self.optimizer.step(self._grad)
+            return hi - lo
+
+        use_graph = self.use_cuda_graph and comm is None and not self.report_loss and steps >= 16
         pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
-        step = 0
-        for _ in range(self.k_epochs):
-            for k in range(n_mb):
-                lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
-                if hi > lo:
-                    grad_fn(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
-                                 returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, self.last_losses[step], self._ws)
-                else:
-                    self._grad.zero_()  # this rank has no rows in minibatch k; it still joins the allreduce
-                if comm is not None:
-                    comm.allreduce_(self._grad)
-                self.optimizer.step(self._grad)
+        if use_graph:
+            # one epoch = n_mb launch triples with fixed pointers: capture once, replay k_epochs times (no host work between
+            # the 3 * steps launches).  last_losses[k] then ACCUMULATES minibatch k's loss sums over the epochs.
+            self.last_losses = t.zeros(n_mb, 4, dtype=t.float64, device=self.device)
+            first_step = self.optimizer.step_count
+            side = self._side_stream = getattr(self, "_side_stream", None) or t.cuda.Stream()
+            side.wait_stream(t.cuda.current_stream())
+            graph = t.cuda.CUDAGraph()
+            with t.cuda.stream(side):
+                graph.capture_begin()   # (torch.cuda.graph() would also synchronise, collect garbage and empty the allocator cache)
+                try:
+                    for k in range(n_mb):
+                        minibatch_step(k, self.last_losses[k])
+                finally:
+                    graph.capture_end()
+            t.cuda.current_stream().wait_stream(side)
+            for _ in range(self.k_epochs):
+                graph.replay()   # AdamW's step number is device-resident, so every replay advances it
                 if pbar is not None:
-                    pbar.update(hi - lo)
-                    if self.report_loss:
-                        l = self.last_losses[step].cpu().numpy()
-                        pbar.set_description(f"Loss: {(l[0] + 0.5 * l[1] - 0.01 * l[2]) / max(l[3], 1.0): .6f}")
-                step += 1
+                    pbar.update(N)
+            self.optimizer.step_count = first_step + steps
+            graphs = graph
+            self._graphs = graphs  # keep alive until the replays have run
+        else:
+            self.last_losses = t.zeros(steps, 4, dtype=t.float64, device=self.device)
+            step = 0
+            for _ in range(self.k_epochs):
+                for k in range(n_mb):
+                    n_rows = minibatch_step(k, self.last_losses[step])
+                    if pbar is not None:
+                        pbar.update(n_rows)
+                        if self.report_loss:
+                            l = self.last_losses[step].cpu().numpy()
+                            pbar.set_description(f"Loss: {(l[0] + 0.5 * l[1] - 0.01 * l[2]) / max(l[3], 1.0): .6f}")
+                    step += 1
         if pbar is not None:
             pbar.close()
         if use_tc and ops.ppo_grad_tc_status(self._ws) != 0:

@@ -66,25 +66,41 @@ k_policy_evaluate(const float *__restrict__ params, PolicyLayout L, const float 
 // =============================================================================================== clip + AdamW
 __global__ void __launch_bounds__(1024)
 k_adamw(float *__restrict__ params, const float *__restrict__ grad, float *__restrict__ m, float *__restrict__ v, int64_t n,
-        int64_t step, float lr, float wd, float max_norm, double *__restrict__ norm_out) {
+        int64_t step, int64_t *__restrict__ step_dev, float lr, float wd, float max_norm, double *__restrict__ norm_out) {
     __shared__ double red[32];
-    __shared__ float coef_s;
+    __shared__ float coef_s, step_size_s, bc2_sqrt_s;
+    // device-resident optimiser clock {step, beta1^step, beta2^step}: the launch is replayable (CUDA graphs) and the bias
+    // corrections cost two multiplications instead of two double-precision pow()
+    double *pows = reinterpret_cast<double *>(step_dev) + 1;
+    if (step_dev) step = *step_dev + 1;
+    // gradient norm: float loads, double accumulation (9 027 values for CartPole: ~9 per thread)
     double ss = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double g = grad[i]; ss += g * g; }
+    const int64_t n4 = n >> 2;
+    const float4 *g4 = reinterpret_cast<const float4 *>(grad);
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 g = g4[i];
+        ss += (double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z + (double)g.w * g.w;
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) ss += (double)grad[i] * grad[i];
     ss = block_sum<double>(ss, red);
     if (threadIdx.x == 0) {
         const float total = (float)sqrt(ss);
-        float c = 1.f;
-        if (max_norm > 0.f) c = fminf(max_norm / (total + 1e-6f), 1.0f);
-        coef_s = c;
+        coef_s = max_norm > 0.f ? fminf(max_norm / (total + 1e-6f), 1.0f) : 1.f;
         if (norm_out) *norm_out = (double)total;
+        // bias corrections once per launch (double pow is expensive; every thread used to evaluate it)
+        double p1, p2;
+        if (step_dev && step > 1 && pows[0] > 0.0) {
+            p1 = pows[0] * 0.9; p2 = pows[1] * 0.999;
+        } else {
+            p1 = pow(0.9, (double)step); p2 = pow(0.999, (double)step);
+        }
+        step_size_s = (float)((double)lr / (1.0 - p1));
+        bc2_sqrt_s = (float)sqrt(1.0 - p2);
+        if (step_dev) { *step_dev = step; pows[0] = p1; pows[1] = p2; }
     }
     __syncthreads();
-    const float coef = coef_s;
+    const float coef = coef_s, step_size = step_size_s, bc2_sqrt = bc2_sqrt_s;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-    const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
     const float decay = 1.0f - lr * wd;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         const float g = grad[i] * coef;
@@ -119,7 +135,14 @@ int prl_policy_evaluate(const float *params, int is_continuous, int obs_dim, int
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step, float lr,
                    float weight_decay, float max_norm, double *grad_norm_out, void *stream) {
     PRL_REQUIRE(params && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "prl_adamw_step: bad arguments");
-    k_adamw<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, step, lr, weight_decay, max_norm, grad_norm_out);
+    k_adamw<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, step, nullptr, lr, weight_decay, max_norm, grad_norm_out);
+    return check_launch("k_adamw");
+}
+
+int prl_adamw_step_dev(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t *step_counter, float lr,
+                       float weight_decay, float max_norm, double *grad_norm_out, void *stream) {
+    PRL_REQUIRE(params && grad && exp_avg && exp_avg_sq && n > 0 && step_counter, "prl_adamw_step_dev: bad arguments");
+    k_adamw<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, exp_avg, exp_avg_sq, n, 0, step_counter, lr, weight_decay, max_norm, grad_norm_out);
     return check_launch("k_adamw");
 }
 

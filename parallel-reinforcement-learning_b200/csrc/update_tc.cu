@@ -576,19 +576,45 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     if (warp == 0) tmem_dealloc(D.tmem, TM_COLS);
 }
 
-// grad[i] = sum over blocks of partials[b][i], fixed order (bit-reproducible); loss_out += block loss partials
-__global__ void k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, float *__restrict__ grad,
-                                     const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x 16 block slices per
+// CTA; slice sl adds blocks sl, sl+16, ... (<= 10 independent loads in flight per thread for <= 160 blocks), and the
+// sixteen slice sums are combined in a fixed tree.  loss_out += block loss partials.
+constexpr int RED_SL = 16, RED_MAX = 10;
+__global__ void __launch_bounds__(64 * RED_SL)
+k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, float *__restrict__ grad,
+                     const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows) {
+    __shared__ float part[RED_SL][64];
+    const int p = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + p;
+    float s = 0.f;
     if (i < P) {
-        float s = 0.f;
-        for (int bl = 0; bl < nblocks; ++bl) s += partials[(size_t)bl * P + i];
-        grad[i] = s;
+        for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
+            float v[RED_MAX];
+#pragma unroll
+            for (int u = 0; u < RED_MAX; ++u) {
+                const int bl = base + u * RED_SL;
+                v[u] = bl < nblocks ? __ldg(partials + (size_t)bl * P + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RED_MAX; ++u) s += v[u];
+        }
+    }
+    part[sl][p] = s;
+    __syncthreads();
+    if (sl == 0 && i < P) {
+        float t[RED_SL];
+#pragma unroll
+        for (int u = 0; u < RED_SL; ++u) t[u] = part[u][p];
+#pragma unroll
+        for (int w = RED_SL / 2; w > 0; w >>= 1)
+#pragma unroll
+            for (int u = 0; u < w; ++u) t[u] += t[u + w];
+        grad[i] = t[0];
     }
     if (blockIdx.x == 0 && threadIdx.x < 3 && loss_out) {
-        double s = 0.0;
-        for (int bl = 0; bl < nblocks; ++bl) s += loss_partials[bl * 4 + threadIdx.x];
-        loss_out[threadIdx.x] += s;
+        double t = 0.0;
+        for (int bl = 0; bl < nblocks; ++bl) t += loss_partials[bl * 4 + threadIdx.x];
+        loss_out[threadIdx.x] += t;
         if (threadIdx.x == 0) loss_out[3] += rows;
     }
 }
@@ -643,7 +669,7 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
     };
     const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
     if (rc != PRL_OK) return rc;
-    k_reduce_partials_tc<<<cdiv(L.total, 256), 256, 0, st>>>(partials, grid, L.total, grad, loss_partials, loss_out, (double)b);
+    k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, grad, loss_partials, loss_out, (double)b);
     return check_launch("k_ppo_grad_tc");
 }
 

@@ -189,11 +189,11 @@ def policy_act(params, is_continuous, O, A, action_scaling, states, seed, call_i
     return (actions, dist) if want_dist else actions
 
 
-def policy_evaluate(params, is_continuous, O, A, states, actions, entropy_sum=None):
+def policy_evaluate(params, is_continuous, O, A, states, actions, entropy_sum=None, logp=None, value=None):
     n = states.shape[0]
     d = _dev()
-    logp = torch.empty(n, dtype=torch.float32, device=d)
-    value = torch.empty(n, dtype=torch.float32, device=d)
+    logp = torch.empty(n, dtype=torch.float32, device=d) if logp is None else logp
+    value = torch.empty(n, dtype=torch.float32, device=d) if value is None else value
     if entropy_sum is None:
         entropy_sum = torch.zeros(1, dtype=torch.float64, device=d)
     call("prl_policy_evaluate", _ptr(params, torch.float32), int(is_continuous), O, A, _ptr(states, torch.float32),
@@ -209,10 +209,11 @@ def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, epi
 
 
 # ------------------------------------------------------------------------------------------------ GAE
-def gae(rewards, dones, values, gamma, gae_lambda, next_value=None, out=None):
+def gae(rewards, dones, values, gamma, gae_lambda, next_value=None, out=None, ws=None):
     N = rewards.numel()
     out = torch.empty(N, dtype=torch.float32, device=_dev()) if out is None else out
-    ws = _ws(_lib.fn("prl_gae_ws_bytes")(N))
+    need = _lib.fn("prl_gae_ws_bytes")(N)
+    ws = _ws(need) if ws is None or ws.numel() < need else ws
     call("prl_gae", _ptr(rewards, torch.float32), _ptr(dones, torch.float32), _ptr(values, torch.float32),
          _ptr(next_value), float(gamma), float(gae_lambda), N, _ptr(out), _ptr(ws), ws.numel(), _stream())
     return out
@@ -277,6 +278,12 @@ def adamw_step(params, grad, exp_avg, exp_avg_sq, step, lr, weight_decay=0.01, m
     call("prl_adamw_step", _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
          _ptr(exp_avg_sq, torch.float32), params.numel(), int(step), float(lr), float(weight_decay), float(max_norm),
          _ptr(grad_norm_out), _stream())
+
+
+def adamw_step_dev(params, grad, exp_avg, exp_avg_sq, step_counter, lr, weight_decay=0.01, max_norm=2.0, grad_norm_out=None):
+    call("prl_adamw_step_dev", _ptr(params, torch.float32), _ptr(grad, torch.float32), _ptr(exp_avg, torch.float32),
+         _ptr(exp_avg_sq, torch.float32), params.numel(), _ptr(step_counter, torch.int64), float(lr), float(weight_decay),
+         float(max_norm), _ptr(grad_norm_out), _stream())
 
 
 def rnd_intrinsic(target_params, pred_params, I, Oo, states, beta, add_to=None, out=None):

@@ -18,12 +18,16 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(flat_params)
         self.exp_avg_sq = torch.zeros_like(flat_params)
         self.step_count = 0
+        # the clock the kernel reads and advances: {int64 step, float64 beta1^step, float64 beta2^step} (zeros = step 0)
+        self.step_dev = torch.zeros(3, dtype=torch.int64, device=flat_params.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float64, device=flat_params.device)  # last pre-clip norm
 
     def step(self, grad: torch.Tensor) -> None:
+        """One optimiser step.  The step number lives in device memory (`step_dev`) so the launch is replayable inside
+        a CUDA graph; `step_count` mirrors it on the host for launches made directly."""
         self.step_count += 1
-        ops.adamw_step(self.params, grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.weight_decay,
-                       self.max_norm, self.grad_norm)
+        ops.adamw_step_dev(self.params, grad, self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr, self.weight_decay,
+                           self.max_norm, self.grad_norm)
 
     def zero_grad(self, set_to_none: bool = True) -> None:  # API compatibility: gradients are produced whole by the kernels
         pass
@@ -34,5 +38,7 @@ class FusedAdamW:
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        self.step_dev.zero_()
+        self.step_dev[0] = self.step_count   # the kernel recomputes the powers when it finds them zero
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

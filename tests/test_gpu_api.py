@@ -96,6 +96,26 @@ def test_learn_matches_reference_post_update_weights(api, golden, name, roll):
         assert (l[0] + 0.5 * l[1] - 0.01 * l[2]) / l[3] == pytest.approx(want, rel=1e-5, abs=1e-6)
 
 
+def test_learn_with_cuda_graph_epochs_is_bit_identical(api):
+    """use_cuda_graph replays one captured epoch k_epochs times (device-resident AdamW step counter): same launches,
+    same order, so the weights must be bit-identical to the launch-by-launch path."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    out = []
+    for graph in (False, True):
+        t.manual_seed(3)
+        ppo = P.PPO(is_continuous=False, observ_dim=4, action_dim=2, k_epochs=5, batch_size=256, mini_batch_size=512)
+        ppo.show_progress = False
+        ppo.use_cuda_graph = graph
+        ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=64), ppo=ppo, num_envs=256, steps=1)
+        ap.worker()
+        assert len(ppo.memory.states) >= 4 * 512   # >= 4 minibatches x 5 epochs = 20 optimiser steps
+        ppo.learn()
+        out.append((ppo.policy.flat.cpu().numpy(), ppo.optimizer.exp_avg_sq.cpu().numpy(), ppo.optimizer.step_count,
+                    int(ppo.optimizer.step_dev[0].item())))
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(bits(out[0][1]), bits(out[1][1]))
+    assert out[0][2] == out[1][2] == out[0][3] == out[1][3] and out[0][2] >= 20
+
+
 def test_learn_returns_early_below_batch_size(api, golden):
     g = golden("learn_discrete")
     ppo = make_ppo(api, g)
