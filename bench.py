@@ -189,6 +189,8 @@ def run_b200(args):
     from prl_b200 import _lib
     from prl_b200 import dist as pdist
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
     comm = pdist.init_from_env()
     rank = comm.rank if comm else 0
     world = comm.world_size if comm else 1

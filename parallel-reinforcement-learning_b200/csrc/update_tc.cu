@@ -4,11 +4,12 @@
 //
 // Reference: /root/reference/PPO/PPO.py:219-252 and PPO/ActorCritic.py:118-146.
 //
-// Work split.  One CTA = 512 threads = one 128-row tile at a time, persistent over tiles.  Row r of the tile is owned
-// by FOUR threads (warps w, w+4, w+8, w+12 share a 32-row quarter; thread q of a row holds features 16q..16q+15 =
-// two GroupNorm groups), so every per-row array is 16 wide and lives in registers, and 16 warps per SM hide latency.
+// Work split.  One CTA = 16 compute warps + 1 MMA-issue warp = one 128-row tile at a time, persistent over tiles.  Row r
+// of the tile is owned by FOUR compute threads (warps w, w+4, w+8, w+12 share a 32-row quarter; thread q of a row holds
+// features 16q..16q+15 = two GroupNorm groups), so every per-row array is 16 wide and lives in registers.
 // Everything that contracts over features or over rows runs as tcgen05.mma (kind::f16 on bf16x3 split operands, fp32
-// accumulators in tensor memory), issued by one elected lane of warp 0:
+// accumulators in tensor memory), issued by one elected lane of warp 16, which does nothing else: the compute warps hand
+// it staged operands through named barriers (arrive, no wait) and only ever wait for MMA completion (mbarriers):
 //     forward   Z[r][(h,j)]  = sum_k F[r][k] W1_h[j][k]          M=128 N=128 K=64    (both heads in one GEMM)
 //     dgrad     DF[r][k]    += sum_j DZ_h[r][j] W1_h[j][k]       M=128 N=64  K=64    (B = MN-major view of the same W1 bytes)
 //     wgrad     DW_h[j][k]  += sum_r DZ_h[r][j] F[r][k]          M=128 N=64  K=128   (A, B = MN-major views of the same DZ / F bytes)
@@ -17,13 +18,16 @@
 // What remains on the CUDA cores are the row-wise nonlinearities (GroupNorm, SiLU, softmax / loss and their backward)
 // and the narrow column sums (GroupNorm affine and output-layer gradients), done as warp butterfly reductions into
 // per-warp register accumulators that are combined once at the end.
+#include <stdlib.h>
+
 #include "policy.cuh"
 #include "umma.cuh"
 
 namespace prl {
 using namespace umma;
 
-constexpr int TC_THREADS = 512, TC_ROWS = 128, TC_W = 16;   // threads, rows per tile, features per thread
+// 16 compute warps + 1 MMA-issue warp; rows per tile; features per thread
+constexpr int TC_COMPUTE = 512, TC_THREADS = TC_COMPUTE + 32, TC_ROWS = 128, TC_W = 16;
 constexpr int PIECE = 8 * CHUNK;     // one bf16 piece of a [128][64] matrix: 8 chunks x 2048 B = 16 KB
 constexpr int XPIECE = 2 * CHUNK;    // one bf16 piece of the [128][16] input matrix
 constexpr int TC_MAX_O = 16, TC_MAX_A = 8;
@@ -125,13 +129,17 @@ __device__ __forceinline__ void load16(const float *src, float (&v)[TC_W]) {
     }
 }
 
-__device__ __forceinline__ void tc_sync_for_mma() {
+// named barrier 1 = the 512 compute threads among themselves (the MMA warp never joins it)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// compute side of an "operands staged" hand-off to the MMA warp: make the shared-memory stores visible to the tensor core
+// (async proxy), then arrive on the hand-off mbarrier (count 512) without waiting
+__device__ __forceinline__ void staged(uint64_t *bar) {
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
+    mbar_arrive(bar);
 }
 
-// ---- MMA issue: all lanes of warp 0 call these (warp-uniform), one elected lane issues --------------------------------
+// ---- MMA issue: all lanes of the MMA warp call these (warp-uniform), one elected lane issues --------------------------------
 struct TcDesc {          // base descriptors, K-major and MN-major views, built once per kernel
     uint64_t F_k, W_k, DZ_k, W_mn, DZ_mn, F_mn, X_mn;
     uint32_t tmem;
@@ -182,22 +190,30 @@ __device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[TC_W]) {
     tmem_ld_wait();
 }
 
+// optional phase timestamps of CTA 0 (PRL_TC_TIMING=1 in the environment prints them after the launch; debugging aid)
+__device__ long long g_tc_clock[32];
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_clock[i] = clock64(); } while (0)
+
 // ===================================================================================================== the kernel
 // NA = compile-time bound of the output widths (action_dim rounded up to 2, 4 or 8): the per-output loops unroll over it
 template <int NA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
-              float clip, float inv_count, float *__restrict__ partials, double *__restrict__ loss_partials, int *__restrict__ status) {
+              float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
+              int *__restrict__ status) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bars[4];          // forward done, actor backward done, critic backward done, trunk wgrad done
+    __shared__ uint64_t bars[4];          // MMA completion: forward, actor backward, critic backward, trunk wgrad
+    __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
     __shared__ uint32_t tmem_slot;
     __shared__ double red[32];
     __shared__ float b2s[4][2][TC_MAX_A];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rq = warp & 3, q = warp >> 2;      // row quarter (= tensor-memory lane quarter), feature quarter
-    const int r = rq * 32 + lane, j0 = TC_W * q; // row of the tile, first feature of this thread
+    const bool is_mma_warp = warp == TC_COMPUTE / 32;
+    const int rq = warp & 3, q = (warp >> 2) & 3;   // row quarter (= tensor-memory lane quarter), feature quarter
+    const int r = rq * 32 + lane, j0 = TC_W * q;    // row of the tile, first feature of this thread
     const int O = L.O, A = L.A;
+    TC_STAMP(0);
 
     // ---- carve shared memory (all pointers derive from smem_raw so they stay in the shared state space)
     unsigned char *sW = smem_raw, *sF = sW + 3 * PIECE, *sDZ = sF + 3 * PIECE, *sX = sDZ + 4 * PIECE;
@@ -220,7 +236,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         stage_copy(sh + 2 * HID, params + L.head[h].w2, L.head[h].out * HID);
         stage_copy(sh + 2 * HID + L.head[h].out * HID, params + L.head[h].b2, L.head[h].out);
     }
-    {
+    if (!is_mma_warp) {
         // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
         const float *wrow = params + L.head[r >> 6].w1 + (r & 63) * HID + j0;
         float v[TC_W];
@@ -234,12 +250,15 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars[i], 1); mbar_init(&sbar[i], TC_COMPUTE); }
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
-    tc_sync_for_mma();
+    if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
     fence_after_sync();
+    TC_STAMP(1);
     TcDesc D;
     D.tmem = tmem_slot;
     D.F_k = smem_desc(smem_u32(sF), CHUNK, 128);
@@ -251,316 +270,354 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     D.X_mn = smem_desc(smem_u32(sX), 128, CHUNK);
     const uint32_t lane_base = D.tmem + ((uint32_t)(rq * 32) << 16);
     bool mma_ok = true;
-
-    // per-warp column-sum accumulators for this thread's two groups (feature f(lane) of each)
-    float q_g0[2] = {0.f, 0.f}, q_b0[2] = {0.f, 0.f};
-    float q_g[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, q_b[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    float q_w2[2][NA][2], q_b2[2][NA];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int a = 0; a < NA; ++a) { q_w2[h][a][0] = q_w2[h][a][1] = 0.f; q_b2[h][a] = 0.f; }
-    double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
-
     const int64_t ntiles = (b + TC_ROWS - 1) / TC_ROWS;
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t parity = it & 1;
-        const int64_t row = tile * TC_ROWS + r;
-        const bool live = row < b;
-        const float *xrow = states + (live ? row : 0) * O;   // dead rows read row 0 and are masked
-        const float xmask = live ? 1.f : 0.f;
+    double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
+    const int P = L.total;
+    float *part = partials + (size_t)blockIdx.x * part_stride;
 
-        // ================= trunk forward (CUDA cores): z0 = W0 x, GroupNorm, SiLU -> F pieces, X pieces
-        float zh0[TC_W], rs0[2];
-        {
-#pragma unroll
-            for (int j = 0; j < TC_W; ++j) zh0[j] = 0.f;
-            for (int i = 0; i < O; ++i) {
-                const float xi = xmask * __ldg(xrow + i);
-                float w[TC_W];
-                load16(s_w0t + i * HID + j0, w);
-#pragma unroll
-                for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(xi, w[j], zh0[j]);
-            }
-            gn_normalize16(zh0, rs0);
-            float f[TC_W], g0w[TC_W], g0b[TC_W];
-            load16(s_g0w + j0, g0w);
-            load16(s_g0b + j0, g0b);
-#pragma unroll
-            for (int j = 0; j < TC_W; ++j) {
-                const float y = fmaf(zh0[j], g0w[j], g0b[j]);
-                f[j] = y * fast_sigmoid(y);
-            }
-            // the previous tile's trunk-wgrad MMAs read X and DZ; its head MMAs (already waited for) read F
-            if (it > 0) mma_ok &= mbar_wait(&bars[3], parity ^ 1);
-            store_pieces16(sF, r, q, f);
-            if (q == 0) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t q0[4], q1[4], q2[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int e = 8 * c + 2 * i;
-                        const float xa = e < O ? xmask * __ldg(xrow + e) : 0.f, xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f;
-                        split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
-                    }
-                    unsigned char *p = sX + c * CHUNK + r * 16;
-                    *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
-                    *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-                    *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
-                }
-            }
-        }
-        tc_sync_for_mma();
-        if (warp == 0) {
+    if (is_mma_warp) {
+        // =============================================================================== MMA-issue warp
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t parity = it & 1;
+            mma_ok &= mbar_wait(&sbar[0], parity);
             fence_after_sync();
-            if (elect_one()) {
-                issue_forward(D);
-                mma_commit(&bars[0]);
-            }
+            if (elect_one()) { issue_forward(D); mma_commit(&bars[0]); }
+            __syncwarp();
+            mma_ok &= mbar_wait(&sbar[1], parity);
+            fence_after_sync();
+            if (elect_one()) { issue_head_backward(D, 0, it == 0); mma_commit(&bars[1]); }
+            __syncwarp();
+            mma_ok &= mbar_wait(&sbar[2], parity);
+            fence_after_sync();
+            if (elect_one()) { issue_head_backward(D, 1, it == 0); mma_commit(&bars[2]); }
+            __syncwarp();
+            mma_ok &= mbar_wait(&sbar[3], parity);
+            fence_after_sync();
+            if (elect_one()) { issue_trunk_wgrad(D, it == 0); mma_commit(&bars[3]); }
             __syncwarp();
         }
-        const float adv_i = live ? adv[row] : 0.f, old_i = live ? old_logp[row] : 0.f;
-        const float ret_i = live ? returns[row] : 0.f;
-        const int act = live ? (int)actions[row] : 0;
-        mma_ok &= mbar_wait(&bars[0], parity);
-        fence_after_sync();
+    } else {
+        // =============================================================================== compute warps
+        // per-warp column-sum accumulators for this thread's two groups (feature f(lane) of each)
+        float q_g0[2] = {0.f, 0.f}, q_b0[2] = {0.f, 0.f};
+        float q_g[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, q_b[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float q_w2[2][NA][2], q_b2[2][NA];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int a = 0; a < NA; ++a) { q_w2[h][a][0] = q_w2[h][a][1] = 0.f; q_b2[h][a] = 0.f; }
 
-        // ================= heads: forward epilogue, loss, backward epilogue -> DZ pieces, tensor-core dgrad + wgrad
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int nout = L.head[h].out;
-            const float *sh = h ? s_head1 : s_head0;
-            const float *w2 = sh + 2 * HID;
-            float gw[TC_W], gb[TC_W];
-            load16(sh + j0, gw);
-            load16(sh + HID + j0, gb);
-            float zhat[TC_W], rstd[2], sg[TC_W];
-            tmem_ld16w(lane_base + TM_Z + 64 * h + j0, zhat);
-            gn_normalize16(zhat, rstd);
-            float po[NA];
-#pragma unroll
-            for (int a = 0; a < NA; ++a) po[a] = 0.f;
-#pragma unroll
-            for (int j = 0; j < TC_W; ++j) {
-                const float y = fmaf(zhat[j], gw[j], gb[j]);
-                sg[j] = fast_sigmoid(y);
-                const float hj = y * sg[j];
-#pragma unroll
-                for (int a = 0; a < NA; ++a)
-                    if (a < nout) po[a] = fmaf(hj, w2[a * HID + j0 + j], po[a]);
-            }
-#pragma unroll
-            for (int a = 0; a < NA; ++a) s_po[(q * TC_ROWS + r) * NA + a] = po[a];
-            __syncthreads();
-            float out[NA];
-#pragma unroll
-            for (int a = 0; a < NA; ++a)
-                out[a] = (a < nout) ? w2[nout * HID + a] + ((s_po[(0 * TC_ROWS + r) * NA + a] + s_po[(1 * TC_ROWS + r) * NA + a]) +
-                                                          (s_po[(2 * TC_ROWS + r) * NA + a] + s_po[(3 * TC_ROWS + r) * NA + a]))
-                                    : 0.f;
-            // ---- loss and output gradients (the four threads of a row compute them redundantly; q == 0 keeps the sums)
-            float dout[NA];
-#pragma unroll
-            for (int a = 0; a < NA; ++a) dout[a] = 0.f;
-            if (h == 0) {
-                if (live) {
-                    float m = out[0];
-#pragma unroll
-                    for (int a = 1; a < NA; ++a)
-                        if (a < A) m = fmaxf(m, out[a]);
-                    float p[NA], Ssum = 0.f, Psum = 0.f;
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) { p[a] = (a < A) ? expf(out[a] - m) : 0.f; Ssum += p[a]; }
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) { p[a] = p[a] / Ssum; Psum += p[a]; }
-                    float pa = 0.f, ent = 0.f;
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) {
-                        if (a < A) {
-                            p[a] = p[a] / Psum;
-                            const float l = logf(fminf(fmaxf(p[a], F32_EPS), 1.0f - F32_EPS));
-                            ent -= l * p[a];
-                            if (a == act) pa = p[a];
-                        }
-                    }
-                    const float logp = logf(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
-                    const float dl = logp - old_i;
-                    const float rr = expf(fminf(fmaxf(dl, -20.f), 20.f));
-                    const float s1 = rr * adv_i;
-                    const float s2 = fminf(fmaxf(rr, 1.0f - clip), 1.0f + clip) * adv_i;
-                    const float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // torch.min splits ties evenly
-                    const float in_clip = (rr >= 1.0f - clip && rr <= 1.0f + clip) ? 1.f : 0.f;
-                    const float in20 = (dl >= -20.f && dl <= 20.f) ? 1.f : 0.f;
-                    float dlogp = -inv_count * adv_i * (g1 + (1.f - g1) * in_clip) * rr * in20;
-                    if (!(pa >= F32_EPS && pa <= 1.0f - F32_EPS)) dlogp = 0.f;   // clamp in probs_to_logits blocks the gradient
-#pragma unroll
-                    for (int a = 0; a < NA; ++a)
-                        if (a < A) dout[a] = dlogp * ((a == act ? 1.f : 0.f) - p[a]);
-                    if (q == 0) { l_pol += -fminf(s1, s2); l_ent += ent; }
-                }
-            } else if (live) {
-                const float dv = out[0] - ret_i, ad = fabsf(dv);
-                if (q == 0) l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
-                dout[0] = 0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f));
-            }
-            // ---- output-layer gradients: dW2[a][j] = sum_r dout[a] h_j, db2[a] = sum_r dout[a]
-#pragma unroll
-            for (int a = 0; a < NA; ++a) {
-                if (a < nout) {
-                    float t[TC_W];
-#pragma unroll
-                    for (int j = 0; j < TC_W; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
-                    colsum16(t, q_w2[h][a]);
-                    if (q == 0) q_b2[h][a] += warp_sum(dout[a]);
-                }
-            }
-            // ---- dy (in place of sg), GroupNorm-affine gradients, GroupNorm backward -> dz
-#pragma unroll
-            for (int j = 0; j < TC_W; ++j) {
-                float dh = 0.f;
-#pragma unroll
-                for (int a = 0; a < NA; ++a)
-                    if (a < nout) dh = fmaf(dout[a], w2[a * HID + j0 + j], dh);
-                const float y = fmaf(zhat[j], gw[j], gb[j]);
-                sg[j] = dh * sg[j] * fmaf(y, 1.0f - sg[j], 1.0f);
-            }
-            {
-                float t[TC_W];
-#pragma unroll
-                for (int j = 0; j < TC_W; ++j) t[j] = sg[j] * zhat[j];
-                colsum16(t, q_g[h]);
-                colsum16(sg, q_b[h]);
-            }
-            gn_backward16(sg, zhat, rstd, gw);   // sg now holds dz
-            // the actor's MMAs read DZ: they must have completed before the critic overwrites it
-            if (h == 1) mma_ok &= mbar_wait(&bars[1], parity);
-            store_pieces16(sDZ, r, q, sg);
-            tc_sync_for_mma();
-            if (warp == 0) {
-                fence_after_sync();
-                if (elect_one()) {
-                    issue_head_backward(D, h, it == 0);
-                    mma_commit(&bars[1 + h]);
-                }
-                __syncwarp();
-            }
-        }
-
-        // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
+        // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
+        constexpr int XR = 8;   // observation values kept in registers (observ_dim > 8 reads the rest on demand)
+        float xn[XR];
         {
-            float df[TC_W], g0w[TC_W], g0b[TC_W];
-            load16(s_g0w + j0, g0w);
-            load16(s_g0b + j0, g0b);
-            mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final; DZ free again
-            fence_after_sync();
-            tmem_ld16w(lane_base + TM_DF + j0, df);
+            const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS + r;
 #pragma unroll
-            for (int j = 0; j < TC_W; ++j) {
-                const float y = fmaf(zh0[j], g0w[j], g0b[j]);
-                const float s = fast_sigmoid(y);
-                df[j] = df[j] * s * fmaf(y, 1.0f - s, 1.0f);
-            }
+            for (int i = 0; i < XR; ++i) xn[i] = (row0 < b && i < O) ? __ldg(states + row0 * O + i) : 0.f;
+        }
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t parity = it & 1;
+            const int64_t row = tile * TC_ROWS + r;
+            const bool live = row < b;
+            const float *xrow = states + (live ? row : 0) * O;   // dead rows read row 0 and are masked
+            const float xmask = live ? 1.f : 0.f;
+            float x[XR];
+#pragma unroll
+            for (int i = 0; i < XR; ++i) x[i] = xn[i];
             {
-                float t[TC_W];
+                const int64_t rown = (tile + gridDim.x) * TC_ROWS + r;
 #pragma unroll
-                for (int j = 0; j < TC_W; ++j) t[j] = df[j] * zh0[j];
-                colsum16(t, q_g0);
-                colsum16(df, q_b0);
+                for (int i = 0; i < XR; ++i) xn[i] = (rown < b && i < O) ? __ldg(states + rown * O + i) : 0.f;
             }
-            gn_backward16(df, zh0, rs0, g0w);
-            store_pieces16(sDZ, r, q, df);
-            tc_sync_for_mma();
-            if (warp == 0) {
-                fence_after_sync();
-                if (elect_one()) {
-                    issue_trunk_wgrad(D, it == 0);
-                    mma_commit(&bars[3]);
-                }
-                __syncwarp();
-            }
-        }
-    }
+            const float adv_i = live ? __ldg(adv + row) : 0.f, old_i = live ? __ldg(old_logp + row) : 0.f;
+            const float ret_i = live ? __ldg(returns + row) : 0.f;
+            const int act = live ? (int)__ldg(actions + row) : 0;
 
-    // ================= read the accumulators out: tensor memory -> this block's partial-gradient row
-    const int P = L.total;
-    float *part = partials + (size_t)blockIdx.x * P;
-    if (it > 0) mma_ok &= mbar_wait(&bars[3], (it - 1) & 1);
-    fence_after_sync();
-    float *scratch = reinterpret_cast<float *>(sF);   // [64][65] + [64][17] fp32 inside the 48 KB F region, free now
-    // DW_h: lanes 0..63 hold the first piece window's products, lanes 64..127 the second's; thread (r, q) reads 16 columns
-    for (int h = 0; h < 2; ++h) {
-        float v[TC_W];
-        tmem_ld16w(lane_base + TM_DW + 64 * h + j0, v);
-        __syncthreads();
-        if (r >= 64) {
+            // ================= trunk forward (CUDA cores): z0 = W0 x, GroupNorm, SiLU -> F pieces, X pieces
+            float zh0[TC_W], rs0[2];
+            {
 #pragma unroll
-            for (int k = 0; k < TC_W; ++k) scratch[(r - 64) * (HID + 1) + j0 + k] = v[k];
-        }
-        __syncthreads();
-        if (r < 64) {
-            float *dst = part + L.head[h].w1 + r * HID + j0;
+                for (int j = 0; j < TC_W; ++j) zh0[j] = 0.f;
 #pragma unroll
-            for (int k = 0; k < TC_W; ++k) dst[k] = (it > 0) ? v[k] + scratch[r * (HID + 1) + j0 + k] : 0.f;
-        }
-    }
-    {
-        float v[TC_W];
-        tmem_ld16w(lane_base + TM_DW0, v);
-        if (q == 0 && r >= 64) {
+                for (int i = 0; i < XR; ++i) {
+                    if (i < O) {
+                        float w[TC_W];
+                        load16(s_w0t + i * HID + j0, w);
 #pragma unroll
-            for (int i = 0; i < TC_W; ++i) scratch[64 * (HID + 1) + (r - 64) * 17 + i] = v[i];
-        }
-        __syncthreads();
-        if (q == 0 && r < 64) {
+                        for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(x[i], w[j], zh0[j]);
+                    }
+                }
+                for (int i = XR; i < O; ++i) {
+                    const float xi = xmask * __ldg(xrow + i);
+                    float w[TC_W];
+                    load16(s_w0t + i * HID + j0, w);
 #pragma unroll
-            for (int i = 0; i < TC_W; ++i)
-                if (i < O) part[L.w0 + r * O + i] = (it > 0) ? v[i] + scratch[64 * (HID + 1) + r * 17 + i] : 0.f;
-        }
-    }
-    // column-sum accumulators: lanes with (lane & 3) == 0 publish feature 16q + 8g + f(lane); combine the four row quarters
-    {
-        __syncthreads();
-        const int NQ = tc_num_q(L);
-        float *r4 = s_red + (size_t)rq * NQ * HID;
-        const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        if ((lane & 3) == 0) {
-            int qq = 0;
-            auto put = [&](const float (&s)[2]) { r4[qq * HID + j0 + f] = s[0]; r4[qq * HID + j0 + 8 + f] = s[1]; ++qq; };
-            put(q_g0); put(q_b0);
+                    for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(xi, w[j], zh0[j]);
+                }
+                gn_normalize16(zh0, rs0);
+                float f[TC_W], g0w[TC_W], g0b[TC_W];
+                load16(s_g0w + j0, g0w);
+                load16(s_g0b + j0, g0b);
+#pragma unroll
+                for (int j = 0; j < TC_W; ++j) {
+                    const float y = fmaf(zh0[j], g0w[j], g0b[j]);
+                    f[j] = y * fast_sigmoid(y);
+                }
+                // the previous tile's trunk-wgrad MMAs read X and DZ; its head MMAs (already waited for) read F
+                if (it > 0) mma_ok &= mbar_wait(&bars[3], parity ^ 1);
+                store_pieces16(sF, r, q, f);
+                if (q == 0) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t q0[4], q1[4], q2[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = 8 * c + 2 * i;
+                            float xa, xb;
+                            if (c == 0) { xa = x[e & 7]; xb = x[(e + 1) & 7]; }
+                            else { xa = e < O ? xmask * __ldg(xrow + e) : 0.f; xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f; }
+                            split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
+                        }
+                        unsigned char *p = sX + c * CHUNK + r * 16;
+                        *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+                        *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+                        *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+                    }
+                }
+            }
+            staged(&sbar[0]);
+            if (it == 0) TC_STAMP(2);
+            mma_ok &= mbar_wait(&bars[0], parity);
+            fence_after_sync();
+            if (it == 0) TC_STAMP(4);
+
+            // ================= heads: forward epilogue, loss, backward epilogue -> DZ pieces, tensor-core dgrad + wgrad
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                put(q_g[h]); put(q_b[h]);
+                const int nout = L.head[h].out;
+                const float *sh = h ? s_head1 : s_head0;
+                const float *w2 = sh + 2 * HID;
+                float gw[TC_W], gb[TC_W];
+                load16(sh + j0, gw);
+                load16(sh + HID + j0, gb);
+                float zhat[TC_W], rstd[2], sg[TC_W];
+                tmem_ld16w(lane_base + TM_Z + 64 * h + j0, zhat);
+                gn_normalize16(zhat, rstd);
+                float po[NA];
+#pragma unroll
+                for (int a = 0; a < NA; ++a) po[a] = 0.f;
+#pragma unroll
+                for (int j = 0; j < TC_W; ++j) {
+                    const float y = fmaf(zhat[j], gw[j], gb[j]);
+                    sg[j] = fast_sigmoid(y);
+                    const float hj = y * sg[j];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+                        if (a < nout) po[a] = fmaf(hj, w2[a * HID + j0 + j], po[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < NA; ++a) s_po[(q * TC_ROWS + r) * NA + a] = po[a];
+                bar_compute();
+                float out[NA];
 #pragma unroll
                 for (int a = 0; a < NA; ++a)
-                    if (a < L.head[h].out) put(q_w2[h][a]);
+                    out[a] = (a < nout) ? w2[nout * HID + a] + ((s_po[(0 * TC_ROWS + r) * NA + a] + s_po[(1 * TC_ROWS + r) * NA + a]) +
+                                                              (s_po[(2 * TC_ROWS + r) * NA + a] + s_po[(3 * TC_ROWS + r) * NA + a]))
+                                        : 0.f;
+                // ---- loss and output gradients (the four threads of a row compute them redundantly; q == 0 keeps the sums)
+                float dout[NA];
+#pragma unroll
+                for (int a = 0; a < NA; ++a) dout[a] = 0.f;
+                if (h == 0) {
+                    if (live) {
+                        float m = out[0];
+#pragma unroll
+                        for (int a = 1; a < NA; ++a)
+                            if (a < A) m = fmaxf(m, out[a]);
+                        float p[NA], Ssum = 0.f, Psum = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) { p[a] = (a < A) ? expf(out[a] - m) : 0.f; Ssum += p[a]; }
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) { p[a] = p[a] / Ssum; Psum += p[a]; }
+                        float pa = 0.f, ent = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) {
+                            if (a < A) {
+                                p[a] = p[a] / Psum;
+                                const float l = logf(fminf(fmaxf(p[a], F32_EPS), 1.0f - F32_EPS));
+                                ent -= l * p[a];
+                                if (a == act) pa = p[a];
+                            }
+                        }
+                        const float logp = logf(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
+                        const float dl = logp - old_i;
+                        const float rr = expf(fminf(fmaxf(dl, -20.f), 20.f));
+                        const float s1 = rr * adv_i;
+                        const float s2 = fminf(fmaxf(rr, 1.0f - clip), 1.0f + clip) * adv_i;
+                        const float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // torch.min splits ties evenly
+                        const float in_clip = (rr >= 1.0f - clip && rr <= 1.0f + clip) ? 1.f : 0.f;
+                        const float in20 = (dl >= -20.f && dl <= 20.f) ? 1.f : 0.f;
+                        float dlogp = -inv_count * adv_i * (g1 + (1.f - g1) * in_clip) * rr * in20;
+                        if (!(pa >= F32_EPS && pa <= 1.0f - F32_EPS)) dlogp = 0.f;   // clamp in probs_to_logits blocks the gradient
+#pragma unroll
+                        for (int a = 0; a < NA; ++a)
+                            if (a < A) dout[a] = dlogp * ((a == act ? 1.f : 0.f) - p[a]);
+                        if (q == 0) { l_pol += -fminf(s1, s2); l_ent += ent; }
+                    }
+                } else if (live) {
+                    const float dv = out[0] - ret_i, ad = fabsf(dv);
+                    if (q == 0) l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
+                    dout[0] = 0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f));
+                }
+                // ---- output-layer gradients: dW2[a][j] = sum_r dout[a] h_j, db2[a] = sum_r dout[a]
+#pragma unroll
+                for (int a = 0; a < NA; ++a) {
+                    if (a < nout) {
+                        float t[TC_W];
+#pragma unroll
+                        for (int j = 0; j < TC_W; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
+                        colsum16(t, q_w2[h][a]);
+                        if (q == 0) q_b2[h][a] += warp_sum(dout[a]);
+                    }
+                }
+                // ---- dy (in place of sg), GroupNorm-affine gradients, GroupNorm backward -> dz
+#pragma unroll
+                for (int j = 0; j < TC_W; ++j) {
+                    float dh = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+                        if (a < nout) dh = fmaf(dout[a], w2[a * HID + j0 + j], dh);
+                    const float y = fmaf(zhat[j], gw[j], gb[j]);
+                    sg[j] = dh * sg[j] * fmaf(y, 1.0f - sg[j], 1.0f);
+                }
+                {
+                    float t[TC_W];
+#pragma unroll
+                    for (int j = 0; j < TC_W; ++j) t[j] = sg[j] * zhat[j];
+                    colsum16(t, q_g[h]);
+                    colsum16(sg, q_b[h]);
+                }
+                gn_backward16(sg, zhat, rstd, gw);   // sg now holds dz
+                if (it == 0) TC_STAMP(5 + 3 * h);
+                // the actor's MMAs read DZ: they must have completed before the critic overwrites it
+                if (h == 1) mma_ok &= mbar_wait(&bars[1], parity);
+                store_pieces16(sDZ, r, q, sg);
+                staged(&sbar[1 + h]);
+                if (it == 0) TC_STAMP(6 + 3 * h);
+            }
+
+            // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
+            {
+                float df[TC_W], g0w[TC_W], g0b[TC_W];
+                load16(s_g0w + j0, g0w);
+                load16(s_g0b + j0, g0b);
+                mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final; DZ free again
+                fence_after_sync();
+                if (it == 0) TC_STAMP(11);
+                tmem_ld16w(lane_base + TM_DF + j0, df);
+#pragma unroll
+                for (int j = 0; j < TC_W; ++j) {
+                    const float y = fmaf(zh0[j], g0w[j], g0b[j]);
+                    const float s = fast_sigmoid(y);
+                    df[j] = df[j] * s * fmaf(y, 1.0f - s, 1.0f);
+                }
+                {
+                    float t[TC_W];
+#pragma unroll
+                    for (int j = 0; j < TC_W; ++j) t[j] = df[j] * zh0[j];
+                    colsum16(t, q_g0);
+                    colsum16(df, q_b0);
+                }
+                gn_backward16(df, zh0, rs0, g0w);
+                store_pieces16(sDZ, r, q, df);
+                staged(&sbar[3]);
+                if (it == 0) TC_STAMP(12);
             }
         }
-        if (q == 0 && lane == 0)
+
+        // ================= read the accumulators out: tensor memory -> this block's partial-gradient row
+        TC_STAMP(13);
+        if (it > 0) mma_ok &= mbar_wait(&bars[3], (it - 1) & 1);
+        fence_after_sync();
+        TC_STAMP(14);
+        float *scratch = reinterpret_cast<float *>(sF);   // [128][68] fp32 = 34 KB inside the 48 KB F region, free now
+        constexpr int SS = HID + 4;
+        // DW_h: lanes 0..63 hold the first piece window's products, lanes 64..127 the second's; thread (r, q) reads 16 columns,
+        // parks them in shared memory, then the CTA writes dW1_h = first + second with coalesced stores
+        for (int h = 0; h < 2; ++h) {
+            float v[TC_W];
+            tmem_ld16w(lane_base + TM_DW + 64 * h + j0, v);
+            bar_compute();
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int a = 0; a < NA; ++a) b2s[rq][h][a] = q_b2[h][a];
-        __syncthreads();
-        for (int idx = tid; idx < NQ * HID; idx += TC_THREADS) {
-            const int qq = idx / HID, j = idx - qq * HID;
-            const float s = (s_red[(0 * NQ + qq) * HID + j] + s_red[(1 * NQ + qq) * HID + j]) + (s_red[(2 * NQ + qq) * HID + j] + s_red[(3 * NQ + qq) * HID + j]);
-            int off;
-            if (qq == 0) off = L.g0w;
-            else if (qq == 1) off = L.g0b;
-            else {
-                int k = qq - 2, h = 0;
-                if (k >= 2 + L.head[0].out) { k -= 2 + L.head[0].out; h = 1; }
-                off = (k == 0) ? L.head[h].gw : (k == 1) ? L.head[h].gb : L.head[h].w2 + (k - 2) * HID;
+            for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<float4 *>(scratch + r * SS + j0 + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            bar_compute();
+            float *dst = part + L.head[h].w1;
+            for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
+                const int j = idx >> 6, k = idx & 63;
+                dst[idx] = (it > 0) ? scratch[j * SS + k] + scratch[(64 + j) * SS + k] : 0.f;
             }
-            part[off + j] = s;
         }
-        if (tid < 2 * NA) {
-            const int h = tid / NA, a = tid % NA;
-            if (a < L.head[h].out) part[L.head[h].b2 + a] = (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]);
+        {
+            float v[TC_W];
+            tmem_ld16w(lane_base + TM_DW0, v);
+            bar_compute();
+            if (q == 0) {
+#pragma unroll
+                for (int i = 0; i < TC_W; ++i) scratch[r * 17 + i] = v[i];
+            }
+            bar_compute();
+            for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
+                const int j = idx / O, i = idx - j * O;
+                part[L.w0 + idx] = (it > 0) ? scratch[j * 17 + i] + scratch[(64 + j) * 17 + i] : 0.f;
+            }
         }
+        // column-sum accumulators: lanes with (lane & 3) == 0 publish feature 16q + 8g + f(lane); combine the four row quarters
+        {
+            bar_compute();
+            const int NQ = tc_num_q(L);
+            float *r4 = s_red + (size_t)rq * NQ * HID;
+            const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0) {
+                int qq = 0;
+                auto put = [&](const float (&sv)[2]) { r4[qq * HID + j0 + f] = sv[0]; r4[qq * HID + j0 + 8 + f] = sv[1]; ++qq; };
+                put(q_g0); put(q_b0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    put(q_g[h]); put(q_b[h]);
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+                        if (a < L.head[h].out) put(q_w2[h][a]);
+                }
+            }
+            if (q == 0 && lane == 0)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) b2s[rq][h][a] = q_b2[h][a];
+            bar_compute();
+            for (int idx = tid; idx < NQ * HID; idx += TC_COMPUTE) {
+                const int qq = idx / HID, j = idx - qq * HID;
+                const float sm = (s_red[(0 * NQ + qq) * HID + j] + s_red[(1 * NQ + qq) * HID + j]) + (s_red[(2 * NQ + qq) * HID + j] + s_red[(3 * NQ + qq) * HID + j]);
+                int off;
+                if (qq == 0) off = L.g0w;
+                else if (qq == 1) off = L.g0b;
+                else {
+                    int k = qq - 2, h = 0;
+                    if (k >= 2 + L.head[0].out) { k -= 2 + L.head[0].out; h = 1; }
+                    off = (k == 0) ? L.head[h].gw : (k == 1) ? L.head[h].gb : L.head[h].w2 + (k - 2) * HID;
+                }
+                part[off + j] = sm;
+            }
+            if (tid < 2 * NA) {
+                const int h = tid / NA, a = tid % NA;
+                if (a < L.head[h].out) part[L.head[h].b2 + a] = (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]);
+            }
+        }
+        TC_STAMP(15);
     }
+    // everyone, the MMA warp included (block_sum synchronises the whole CTA)
     const double bp = block_sum<double>(l_pol, red);
     const double bv = block_sum<double>(l_val, red);
     const double be = block_sum<double>(l_ent, red);
@@ -571,9 +628,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         loss_partials[blockIdx.x * 4 + 3] = 0.0;
     }
     if (!mma_ok && lane == 0) atomicExch(status, 1);
+    (void)P;
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(D.tmem, TM_COLS);
+    if (is_mma_warp) tmem_dealloc(D.tmem, TM_COLS);
+    TC_STAMP(16);
 }
 
 // grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x 16 block slices per
@@ -581,7 +640,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 // sixteen slice sums are combined in a fixed tree.  loss_out += block loss partials.
 constexpr int RED_SL = 16, RED_MAX = 10;
 __global__ void __launch_bounds__(64 * RED_SL)
-k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, float *__restrict__ grad,
+k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int stride, float *__restrict__ grad,
                      const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows) {
     __shared__ float part[RED_SL][64];
     const int p = threadIdx.x & 63, sl = threadIdx.x >> 6;
@@ -593,7 +652,7 @@ k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, flo
 #pragma unroll
             for (int u = 0; u < RED_MAX; ++u) {
                 const int bl = base + u * RED_SL;
-                v[u] = bl < nblocks ? __ldg(partials + (size_t)bl * P + i) : 0.f;
+                v[u] = bl < nblocks ? __ldg(partials + (size_t)bl * stride + i) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < RED_MAX; ++u) s += v[u];
@@ -640,7 +699,7 @@ int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim) {
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(batch);
-    return 4 + (size_t)grid * L.total + (size_t)grid * 8 + 16;
+    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + 16;
 }
 
 int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
@@ -652,7 +711,9 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
                 TC_MAX_A, is_continuous, obs_dim, action_dim);
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(b);
-    PRL_REQUIRE(ws_floats >= 4 + (size_t)grid * L.total + (size_t)grid * 8 + 16, "prl_ppo_grad_tc: workspace too small");
+    const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
+    PRL_REQUIRE(ws_floats >= 4 + (size_t)grid * pstride + (size_t)grid * 8 + 16, "prl_ppo_grad_tc: workspace too small");
+    PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "prl_ppo_grad_tc: workspace must be 16-byte aligned");
     const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
     const size_t smem = tc_smem_bytes(L, NA);
     PRL_REQUIRE(smem <= 227 * 1024, "prl_ppo_grad_tc: needs %zu B shared memory (> 227 KB)", smem);
@@ -660,16 +721,26 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
     // ws[0] = sticky status word (the caller zeroes the workspace once), then the per-block partial gradients and losses
     int *status = reinterpret_cast<int *>(ws);
     float *partials = ws + 4;
-    double *loss_partials = reinterpret_cast<double *>(partials + (((size_t)grid * L.total + 1) & ~(size_t)1));
+    double *loss_partials = reinterpret_cast<double *>(partials + (size_t)grid * pstride);
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, TC_THREADS, smem, st>>>(params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials,
+        kernel<<<grid, TC_THREADS, smem, st>>>(params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
                                              loss_partials, status);
         return PRL_OK;
     };
     const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
     if (rc != PRL_OK) return rc;
-    k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, grad, loss_partials, loss_out, (double)b);
+    if (getenv("PRL_TC_TIMING")) {
+        long long c[32];
+        PRL_CUDA(cudaStreamSynchronize(st));
+        PRL_CUDA(cudaMemcpyFromSymbol(c, g_tc_clock, sizeof c));
+        fprintf(stderr, "[prl_ppo_grad_tc] CTA0 thread 0 cycles: setup %lld | tile 0: trunk fwd + stage F %lld, wait fwd MMA %lld, actor epilogue %lld, stage DZ %lld, "
+                        "critic epilogue %lld, wait actor MMA + stage DZ %lld, wait critic MMA %lld, trunk bwd + stage %lld | all tiles %lld, final MMA wait %lld, "
+                        "readout %lld, tail %lld | kernel %lld\n",
+                c[1] - c[0], c[2] - c[1], c[4] - c[2], c[5] - c[4], c[6] - c[5], c[8] - c[6], c[9] - c[8], c[11] - c[9], c[12] - c[11], c[13] - c[1],
+                c[14] - c[13], c[15] - c[14], c[16] - c[15], c[16] - c[0]);
+    }
+    k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
     return check_launch("k_ppo_grad_tc");
 }
 
