@@ -291,6 +291,7 @@ def run_b200(args):
             gbs = (n_prof / world) * b / (per[name]["ms"] * 1e-3) / 1e9
             hbm[name] = {"GB/s": gbs, "frac_of_" + pk["source"] + "_hbm": gbs / pk["hbm"], "bytes_per_transition": b, "ms": per[name]["ms"], "calls": per[name]["calls"]}
 
+    micro = hbm_microbench(pk) if rank == 0 else None
     if rank != 0:
         return
     out = {
@@ -306,6 +307,7 @@ def run_b200(args):
         "clocks": clk,
         "roofline": roof,
         "hbm_kernels": hbm,
+        "hbm_micro": micro,
         "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -315,6 +317,70 @@ def run_b200(args):
                                "sample": f"1 step of {args.cpu_sample_envs} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
                                          f"{cs} env-steps in {csec:.1f} s"}
     print(json.dumps(out))
+
+
+def hbm_microbench(pk, E=65536, T=128):
+    """The HBM-bound kernels of the path in isolation (outside the timed region): achieved GB/s at SURVEY 8(d)'s
+    algorithmic bytes per unit, CUDA events on the launching stream, inputs larger than L2 or L2 flushed between calls."""
+    import numpy as np
+    import torch as t
+
+    from prl_b200 import ops
+
+    dev = t.device("cuda", t.cuda.current_device())
+    flush = t.empty(256 << 20, dtype=t.uint8, device=dev)
+
+    def timeit(fn, reps=8):
+        fn()
+        ms = 0.0
+        for _ in range(reps):
+            flush.fill_(0)
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            t.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms / reps
+
+    out = {}
+    N = E * T
+    r = t.ones(N, device=dev); v = t.rand(N, device=dev); ret = t.empty(N, device=dev); adv = t.empty(N, device=dev)
+    for name, ep in (("gae_flat_T128", T), ("gae_flat_T20", 20)):
+        d = t.zeros(N, device=dev); d[ep - 1::ep] = 1.0
+        ms = timeit(lambda: ops.gae(r, d, v, 0.995, 0.95, out=ret))
+        out[name] = {"GB/s": N * 16 / ms / 1e6, "ms": ms, "bytes_per_transition": 16}
+    r2, d2, v2 = r.view(T, E), t.zeros(T, E, device=dev), v.view(T, E)
+    d2[T - 1] = 1.0
+    lens = t.full((E,), T, dtype=t.int32, device=dev)
+    ms = timeit(lambda: ops.gae_columns(r2, d2, v2, lens, 0.995, 0.95, out=ret.view(T, E)))
+    out["gae_columns_T128"] = {"GB/s": N * 16 / ms / 1e6, "ms": ms, "bytes_per_transition": 16}
+    stats = t.zeros(4, dtype=t.float64, device=dev)
+    ms = timeit(lambda: (stats.zero_(), ops.adv_normalize(ret, v, stats=stats, phase=3, out=adv)))
+    out["adv_normalize"] = {"GB/s": N * 20 / ms / 1e6, "ms": ms, "bytes_per_transition": 20}
+    # standalone env step (per-step API), all envs active, 2^20 envs: 102 B per env-step (CartPole)
+    E2 = 1 << 20
+    sim = ops.EnvState("CartPole-v1", E2, 1 << 30)
+    sim.reset(1, 1)
+    idx = t.arange(E2, dtype=t.int32, device=dev)
+    acts = t.randint(0, 2, (E2,), dtype=t.int32, device=dev)
+    ms = timeit(lambda: sim.step(idx, E2, acts))
+    out["env_step_cartpole"] = {"GB/s": E2 * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "envs": E2}
+    # teacher-forced fused rollout (physics + TimeLimit + mask + buffer write, no policy): E x T env-steps
+    sim = ops.EnvState("CartPole-v1", E, T)
+    buf = ops.RolloutBuffer(E, T, 4, 1)
+    tape = t.randint(0, 2, (T, E), dtype=t.int32, device=dev)
+    scores = t.zeros(2, dtype=t.float64, device=dev)
+    steps = [0.0]
+
+    def taped():
+        sim.reset(1, 1)
+        scores.zero_()
+        ops.rollout(sim, buf, None, 1.0, 0, 1, scores, tape=tape)
+    ms = timeit(taped)
+    n_steps = float(scores.cpu()[1])
+    out["rollout_taped_cartpole"] = {"GB/s": n_steps * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "env_steps": n_steps}
+    for k in out:
+        out[k]["frac_of_" + pk["source"] + "_hbm"] = out[k]["GB/s"] / pk["hbm"]
+    return out
 
 
 def main():

@@ -20,6 +20,10 @@ __device__ __forceinline__ float gae_step(float r, float d, float v, float nv, f
     return __fadd_rn(gae, v);
 }
 
+// U time steps of loads are issued together before the (strictly sequential) arithmetic of those steps retires: with one
+// thread per env there are only ~14 warps per SM at E = 65 536, so memory-level parallelism has to come from each thread
+// (3 loads x U x 128 B per warp in flight).
+constexpr int GCU = 8;
 __global__ void __launch_bounds__(256)
 k_gae_columns(const float *__restrict__ rewards, const float *__restrict__ dones, const float *__restrict__ values,
               const int32_t *__restrict__ lengths, int E, int T_cap, float g, float gl, float *__restrict__ returns) {
@@ -29,82 +33,126 @@ k_gae_columns(const float *__restrict__ rewards, const float *__restrict__ dones
     if (len <= 0) return;
     float gae = 0.f;
     float nv = values[(size_t)(len - 1) * E + e];
-    // software prefetch one step ahead: the three loads of step t-1 are issued before step t's arithmetic retires
-    size_t i = (size_t)(len - 1) * E + e;
-    float r = rewards[i], d = dones[i], v = values[i];
-    for (int t = len - 1; t >= 0; --t) {
-        float r2 = 0.f, d2 = 0.f, v2 = 0.f;
-        if (t > 0) {
-            const size_t j = i - E;
-            r2 = rewards[j]; d2 = dones[j]; v2 = values[j];
+    for (int t0 = len - 1; t0 >= 0; t0 -= GCU) {
+        float r[GCU], d[GCU], v[GCU];
+#pragma unroll
+        for (int u = 0; u < GCU; ++u) {
+            const int t = t0 - u;
+            const size_t i = (size_t)(t < 0 ? 0 : t) * E + e;
+            r[u] = rewards[i]; d[u] = dones[i]; v[u] = values[i];
         }
-        returns[i] = gae_step(r, d, v, nv, g, gl, gae);
-        nv = v;
-        r = r2; d = d2; v = v2;
-        i -= E;
+#pragma unroll
+        for (int u = 0; u < GCU; ++u) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                returns[(size_t)t * E + e] = gae_step(r[u], d[u], v[u], nv, g, gl, gae);
+                nv = v[u];
+            }
+        }
     }
 }
 
 // ---- flat form ---------------------------------------------------------------------------------------------------
-constexpr int SEG_TPB = 1024;
+// One CTA per chunk of GC consecutive transitions.  The chunk's rewards / dones / values are loaded into shared memory
+// with coalesced loads, the segment ends inside the chunk are compacted (warp ballots), each thread then walks one
+// segment backwards IN SHARED MEMORY in the reference's operation order, and the returns leave with coalesced stores.
+// A chunk owns exactly the segments that END in it: the first of them may begin in an earlier chunk - its owner follows
+// it back through global memory (rare: one segment per chunk); elements after the chunk's last end belong to a later chunk.
+constexpr int GC = 4096, GT = 256;
+// shared-memory index of chunk element i: one pad word per 32 and per 128 elements, so that threads walking segments
+// whose starts are 32, 64, 128, ... elements apart (equal-length episodes) hit different banks
+__device__ __forceinline__ int gpad(int i) { return i + (i >> 5) + (i >> 7); }
+constexpr int GCP = GC + GC / 32 + GC / 128;
 
-__device__ __forceinline__ int is_seg_end(const float *__restrict__ dones, int64_t i, int64_t N) {
-    return (i < N) && (dones[i] != 0.f || i == N - 1);
-}
-
-__global__ void k_seg_counts(const float *__restrict__ dones, int64_t N, int32_t *__restrict__ counts) {
-    __shared__ int32_t sc[32];
-    const int64_t i = (int64_t)blockIdx.x * SEG_TPB + threadIdx.x;
-    const int c = block_sum<int32_t>(is_seg_end(dones, i, N), sc);
-    if (threadIdx.x == 0) counts[blockIdx.x] = c;
-}
-
-__global__ void k_seg_ends(const float *__restrict__ dones, int64_t N, const int32_t *__restrict__ counts,
-                           int64_t *__restrict__ ends, int64_t *__restrict__ nseg) {
-    __shared__ int64_t sc64[32];
-    __shared__ int32_t wsum[32];
-    __shared__ int64_t base_s;
-    int64_t part = 0;
-    for (int j = threadIdx.x; j < (int)blockIdx.x; j += blockDim.x) part += counts[j];
-    part = block_sum<int64_t>(part, sc64);
-    if (threadIdx.x == 0) base_s = part;
-    __syncthreads();
-    const int64_t base = base_s;
-    const int64_t i = (int64_t)blockIdx.x * SEG_TPB + threadIdx.x;
-    const int f = is_seg_end(dones, i, N);
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) wsum[w] = __popc(bal);
-    __syncthreads();
-    if (w == 0) {
-        int v = wsum[lane], incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+__global__ void __launch_bounds__(GT)
+k_gae_chunks(const float *__restrict__ rewards, const float *__restrict__ dones, const float *__restrict__ values,
+             const float *__restrict__ next_value_ptr, int64_t N, float g, float gl, float *__restrict__ returns) {
+    extern __shared__ __align__(16) float gsm[];
+    float *sr = gsm, *sd = sr + GCP, *sv = sd + GCP;   // the return of element i overwrites sr[i] once r[i] has been used
+    uint16_t *ends = reinterpret_cast<uint16_t *>(sv + GCP);
+    __shared__ int wcount[GT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * GC;
+    const int len = (int)min((int64_t)GC, N - c0);
+    const bool vec = (((uintptr_t)rewards | (uintptr_t)dones | (uintptr_t)values) & 15) == 0 && len == GC;
+    if (vec) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(rewards + c0), *d4 = reinterpret_cast<const float4 *>(dones + c0),
+                     *v4 = reinterpret_cast<const float4 *>(values + c0);
+#pragma unroll 4
+        for (int i = tid; i < GC / 4; i += GT) {
+            const float4 a = r4[i], bq = d4[i], c = v4[i];
+            const int p = gpad(4 * i);   // 4 consecutive elements never straddle a pad word (pads follow multiples of 32)
+            sr[p] = a.x; sr[p + 1] = a.y; sr[p + 2] = a.z; sr[p + 3] = a.w;
+            sd[p] = bq.x; sd[p + 1] = bq.y; sd[p + 2] = bq.z; sd[p + 3] = bq.w;
+            sv[p] = c.x; sv[p + 1] = c.y; sv[p + 2] = c.z; sv[p + 3] = c.w;
         }
-        wsum[lane] = incl - v;
-        if (lane == 31 && blockIdx.x == gridDim.x - 1) *nseg = base + incl;
+    } else {
+        for (int i = tid; i < len; i += GT) {
+            const int p = gpad(i);
+            sr[p] = rewards[c0 + i];
+            sd[p] = dones[c0 + i];
+            sv[p] = values[c0 + i];
+        }
     }
     __syncthreads();
-    if (f) ends[base + wsum[w] + __popc(bal & ((1u << lane) - 1))] = i;
-}
-
-__global__ void __launch_bounds__(128)
-k_gae_segments(const float *__restrict__ rewards, const float *__restrict__ dones, const float *__restrict__ values,
-               const float *__restrict__ next_value_ptr, const int64_t *__restrict__ ends, const int64_t *__restrict__ nseg,
-               int64_t N, float g, float gl, float *__restrict__ returns) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= *nseg) return;
-    const int64_t end = ends[k];
-    const int64_t start = k > 0 ? ends[k - 1] + 1 : 0;
-    float nv = (end == N - 1) ? (next_value_ptr ? *next_value_ptr : values[N - 1]) : values[end + 1];
-    float gae = 0.f;
-    for (int64_t t = end; t >= start; --t) {
-        const float v = values[t];
-        returns[t] = gae_step(rewards[t], dones[t], v, nv, g, gl, gae);
-        nv = v;
+    // ---- compact the segment ends of the chunk, ascending
+    int nends = 0;
+    for (int it = 0; it < GC / GT; ++it) {
+        const int i = it * GT + tid;
+        const bool f = i < len && (sd[gpad(i)] != 0.f || c0 + i == N - 1);
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcount[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < GT / 32; ++j) {
+            const int c = wcount[j];
+            before += j < w ? c : 0;
+            total += c;
+        }
+        if (f) ends[nends + before + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
+        nends += total;
+        __syncthreads();
     }
+    // ---- one segment per thread
+    for (int k = tid; k < nends; k += GT) {
+        const int e = ends[k], s = k ? ends[k - 1] + 1 : 0;
+        const int64_t ge = c0 + e;
+        float nv = (ge == N - 1) ? (next_value_ptr ? *next_value_ptr : values[N - 1]) : (e + 1 < len ? sv[gpad(e + 1)] : values[ge + 1]);
+        float gae = 0.f;
+        // 8 steps of shared-memory loads and of the gae-independent part (delta) are in flight per iteration; only
+        // gae = delta + (gl * nd) * gae is a serial chain
+        int t = e;
+        for (; t - 7 >= s; t -= 8) {
+            float r8[8], d8[8], v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = gpad(t - u);
+                r8[u] = sr[p]; d8[u] = sd[p]; v8[u] = sv[p];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                sr[gpad(t - u)] = gae_step(r8[u], d8[u], v8[u], nv, g, gl, gae);
+                nv = v8[u];
+            }
+        }
+        for (; t >= s; --t) {
+            const int p = gpad(t);
+            const float v = sv[p];
+            sr[p] = gae_step(sr[p], sd[p], v, nv, g, gl, gae);
+            nv = v;
+        }
+        if (k == 0) {   // the part of this segment that lies in earlier chunks
+            for (int64_t t = c0 - 1; t >= 0 && dones[t] == 0.f; --t) {
+                const float v = values[t];
+                returns[t] = gae_step(rewards[t], 0.f, v, nv, g, gl, gae);
+                nv = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int last = nends ? ends[nends - 1] : -1;
+    for (int i = tid; i <= last; i += GT) returns[c0 + i] = sr[gpad(i)];
 }
 
 // ---- advantage normalisation -------------------------------------------------------------------------------------
@@ -168,26 +216,21 @@ using namespace prl;
 extern "C" {
 
 size_t prl_gae_ws_bytes(int64_t N) {
-    return (size_t)(cdiv(N, SEG_TPB) + 2) * sizeof(int32_t) + 16 + (size_t)(N + 2) * sizeof(int64_t);
+    (void)N;
+    return 16;   // the chunked kernel needs no workspace; the parameter stays in the ABI
 }
 
 int prl_gae(const float *rewards, const float *dones, const float *values, const float *next_value_ptr, double gamma,
             double gae_lambda, int64_t N, float *returns, void *ws, size_t ws_bytes, void *stream) {
+    (void)ws; (void)ws_bytes;
     PRL_REQUIRE(N >= 0, "prl_gae: negative N");
     if (N == 0) return PRL_OK;
-    PRL_REQUIRE(rewards && dones && values && returns && ws && ws_bytes >= prl_gae_ws_bytes(N), "prl_gae: null pointer or workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int nb = cdiv(N, SEG_TPB);
-    int32_t *counts = static_cast<int32_t *>(ws);
-    char *p = static_cast<char *>(ws) + (((size_t)(nb + 2) * sizeof(int32_t) + 7) & ~(size_t)7);
-    int64_t *nseg = reinterpret_cast<int64_t *>(p);
-    int64_t *ends = nseg + 1;
-    k_seg_counts<<<nb, SEG_TPB, 0, st>>>(dones, N, counts);
-    k_seg_ends<<<nb, SEG_TPB, 0, st>>>(dones, N, counts, ends, nseg);
-    // at most N segments; launch for the worst case, threads beyond *nseg exit
-    k_gae_segments<<<cdiv(N, 128), 128, 0, st>>>(rewards, dones, values, next_value_ptr, ends, nseg, N, (float)gamma,
-                                                (float)(gamma * gae_lambda), returns);
-    return check_launch("k_gae_segments");
+    PRL_REQUIRE(rewards && dones && values && returns, "prl_gae: null pointer");
+    const size_t smem = (size_t)3 * GCP * sizeof(float) + (size_t)GC * sizeof(uint16_t);
+    PRL_CUDA(cudaFuncSetAttribute(k_gae_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gae_chunks<<<cdiv(N, GC), GT, smem, (cudaStream_t)stream>>>(rewards, dones, values, next_value_ptr, N, (float)gamma,
+                                                               (float)(gamma * gae_lambda), returns);
+    return check_launch("k_gae_chunks");
 }
 
 int prl_gae_columns(const float *rewards, const float *dones, const float *values, const int32_t *lengths, int E, int T_cap,

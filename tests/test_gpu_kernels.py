@@ -208,7 +208,8 @@ def test_gae_flat_matches_reference_golden(ops, golden, name):
 
 def test_gae_flat_random_segments_bit_exact(ops):
     rng = np.random.default_rng(2)
-    for N, p_done in [(1, 0.5), (257, 0.0), (100_003, 0.02), (300_000, 0.2)]:
+    # short and long segments; the last cases have segments spanning several 4 096-element chunks of the kernel
+    for N, p_done in [(1, 0.5), (257, 0.0), (4096, 0.01), (4097, 0.0), (100_003, 0.02), (300_000, 0.2), (200_001, 0.0005), (50_000, 0.0)]:
         r = rng.standard_normal(N).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
         d = (rng.random(N) < p_done).astype(np.float32)
         want = cref.gae(r, d, v, v[-1], 0.995, 0.95)
