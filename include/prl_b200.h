@@ -155,6 +155,15 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
                     float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
                     void *stream);
 int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream);
+/* prl_ppo_grad_tc + clip_grad_norm_ + AdamW in ONE cooperative launch (single-GPU path): after the per-CTA partial
+ * gradients are written, a grid barrier, a fixed-order reduction of each CTA's slice of the parameters, a second
+ * barrier for the squared norm, then the AdamW update of `params` in place.  `grad` receives the reduced gradient,
+ * step_counter is the 24-byte optimiser clock of prl_adamw_step_dev.  Status word 2 = a grid barrier timed out. */
+int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
+                    const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
+                    float policy_clip, float inv_count, float *grad, double *loss_out, float *exp_avg,
+                    float *exp_avg_sq, int64_t *step_counter, float lr, float weight_decay, float max_norm,
+                    double *grad_norm_out, float *ws, size_t ws_floats, void *stream);
 /* nn.utils.clip_grad_norm_(params, max_norm) + AdamW.step (PPO.py:250-252; torch defaults betas (0.9,0.999),
  * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,

@@ -86,6 +86,7 @@ class PPO:
         self._rows = None
         # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies), "fp32" = CUDA-core
         # FMA kernel (csrc/update_ppo.cu; every configuration).  Same math and tolerances, two members of one family.
+        self.fused_optimizer = True   # tensor path, single process: one launch per optimiser step (prl_ppo_step_tc)
         self.use_cuda_graph = False   # capture each epoch of learn() in a CUDA graph (single process, >= 16 optimiser steps)
         self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
 
@@ -185,8 +186,15 @@ class PPO:
             self._ws = t.zeros(need, dtype=t.float32, device=self.device)
         steps = self.k_epochs * n_mb
 
+        fused = use_tc and comm is None and self.fused_optimizer   # gradient + clip + AdamW in one cooperative launch
+
         def minibatch_step(k, loss_slot):
             lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
+            if fused:
+                ops.ppo_step_tc(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
+                                returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, loss_slot, self.optimizer, self._ws)
+                self.optimizer.step_count += 1
+                return hi - lo
             if hi > lo:
                 grad_fn(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
                         returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, loss_slot, self._ws)

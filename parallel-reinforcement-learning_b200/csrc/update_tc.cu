@@ -190,6 +190,63 @@ __device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[TC_W]) {
     tmem_ld_wait();
 }
 
+// Fused optimiser tail (single-GPU path): after a grid-wide barrier every CTA reduces its slice of the parameters over
+// all CTAs' partial gradients (fixed order), a second barrier makes the squared-norm partials visible, then every CTA
+// applies clip_grad_norm_ + AdamW to its slice.  One launch per optimiser step instead of three.
+struct TcOptimizer {
+    float *params_rw, *grad, *m, *v;          // params_rw == nullptr: gradient only (the reduction runs as a separate kernel)
+    int64_t *clock;                           // {int64 step, double beta1^step, double beta2^step}
+    unsigned int *sync;                       // two zeroed counters (grid barriers)
+    double *sumsq;                            // [grid] squared-norm partials
+    double *norm_out;
+    float lr, wd, max_norm;
+    double *loss_out;                         // 4 doubles, accumulated
+    double rows;
+};
+
+// grid-wide barrier for a grid whose CTAs are all resident (cooperative launch): bounded spin, false on time-out
+__device__ __forceinline__ bool grid_barrier(unsigned int *counter, unsigned int nblocks) {
+    __syncthreads();
+    __shared__ int ok_s;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        int ok = 0;
+        for (int it = 0; it < (1 << 24); ++it) {
+            unsigned int c;
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(c) : "l"(counter) : "memory");
+            if (c >= nblocks) { ok = 1; break; }
+        }
+        ok_s = ok;
+    }
+    __syncthreads();
+    return ok_s != 0;
+}
+
+// sum over the CTAs' partial rows of parameter i, slice sl of RED_SL (blocks sl, sl + RED_SL, ... in ascending order)
+constexpr int RED_SL = 16, RED_MAX = 10;
+__device__ __forceinline__ float reduce_slice(const float *__restrict__ partials, int nblocks, int stride, int i, int sl) {
+    float s = 0.f;
+    for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
+        float v[RED_MAX];
+#pragma unroll
+        for (int u = 0; u < RED_MAX; ++u) {
+            const int bl = base + u * RED_SL;
+            v[u] = bl < nblocks ? __ldcg(partials + (size_t)bl * stride + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < RED_MAX; ++u) s += v[u];
+    }
+    return s;
+}
+__device__ __forceinline__ float reduce_tree(float (&t)[RED_SL]) {
+#pragma unroll
+    for (int w = RED_SL / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int u = 0; u < w; ++u) t[u] += t[u + w];
+    return t[0];
+}
+
 // optional phase timestamps of CTA 0 (PRL_TC_TIMING=1 in the environment prints them after the launch; debugging aid)
 __device__ long long g_tc_clock[32];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_clock[i] = clock64(); } while (0)
@@ -201,7 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
               float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
-              int *__restrict__ status) {
+              int *__restrict__ status, TcOptimizer opt) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bars[4];          // MMA completion: forward, actor backward, critic backward, trunk wgrad
     __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
@@ -275,6 +332,16 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
     const int P = L.total;
     float *part = partials + (size_t)blockIdx.x * part_stride;
+    // optimiser clock, read before anybody can advance it (CTA 0 does, after the second grid barrier)
+    int64_t opt_step = 0;
+    double opt_p1 = 0.0, opt_p2 = 0.0;
+    if (opt.params_rw) {
+        opt_step = opt.clock[0] + 1;
+        const double *pw = reinterpret_cast<const double *>(opt.clock) + 1;
+        const bool have = opt_step > 1 && pw[0] > 0.0;
+        opt_p1 = have ? pw[0] * 0.9 : pow(0.9, (double)opt_step);
+        opt_p2 = have ? pw[1] * 0.999 : pow(0.999, (double)opt_step);
+    }
 
     if (is_mma_warp) {
         // =============================================================================== MMA-issue warp
@@ -628,47 +695,101 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         loss_partials[blockIdx.x * 4 + 3] = 0.0;
     }
     if (!mma_ok && lane == 0) atomicExch(status, 1);
-    (void)P;
     fence_before_sync();
     __syncthreads();
     if (is_mma_warp) tmem_dealloc(D.tmem, TM_COLS);
     TC_STAMP(16);
+    if (!opt.params_rw) return;
+
+    // ================= fused optimiser tail: reduce -> clip_grad_norm_ -> AdamW on this CTA's slice of the parameters
+    const int nb = gridDim.x;
+    if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    const int S = (P + nb - 1) / nb, i0 = blockIdx.x * S, n_i = max(0, min(S, P - i0));   // 61 for P = 9 027 on 148 CTAs
+    constexpr int RC = 64;                                            // parameters reduced per pass
+    float *sl_part = reinterpret_cast<float *>(smem_raw);             // [RED_SL][RC] slice sums
+    double *sq = reinterpret_cast<double *>(smem_raw + 8192);         // [RC] squared gradients
+    double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slice
+    for (int c0 = 0; c0 < n_i; c0 += RC) {
+        const int nc = min(RC, n_i - c0);
+        for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
+            const int sl = item / nc, pi = item - sl * nc;
+            sl_part[sl * RC + pi] = reduce_slice(partials, nb, part_stride, i0 + c0 + pi, sl);
+        }
+        __syncthreads();
+        if (tid < nc) {
+            float t16[RED_SL];
+#pragma unroll
+            for (int u = 0; u < RED_SL; ++u) t16[u] = sl_part[u * RC + tid];
+            const float gi = reduce_tree(t16);
+            opt.grad[i0 + c0 + tid] = gi;
+            sq[tid] = (double)gi * gi;
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int k = 0; k < nc; ++k) ssum += sq[k];
+    }
+    if (tid == 0) {
+        opt.sumsq[blockIdx.x] = ssum;
+        if (blockIdx.x == 0) {   // losses of the whole launch (same bookkeeping as k_reduce_partials_tc); the other CTAs'
+            // loss partials are visible: they were written before the first grid barrier
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int bl = 0; bl < nb; ++bl) { a0 += loss_partials[bl * 4]; a1 += loss_partials[bl * 4 + 1]; a2 += loss_partials[bl * 4 + 2]; }
+            if (opt.loss_out) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
+        }
+    }
+    if (!grid_barrier(opt.sync + 1, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    __shared__ float coef_s;
+    if (warp == 0) {
+        // total squared norm in a fixed order: lane l adds partials l, l + 32, ...; then a fixed shuffle tree
+        double a = 0.0;
+        for (int k = lane; k < nb; k += 32) a += __ldcg(opt.sumsq + k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            const float total = (float)sqrt(a);
+            coef_s = opt.max_norm > 0.f ? fminf(opt.max_norm / (total + 1e-6f), 1.0f) : 1.f;
+            if (blockIdx.x == 0) {
+                if (opt.norm_out) *opt.norm_out = (double)total;
+                double *pw = reinterpret_cast<double *>(opt.clock) + 1;
+                opt.clock[0] = opt_step; pw[0] = opt_p1; pw[1] = opt_p2;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+        const float step_size = (float)((double)opt.lr / (1.0 - opt_p1)), bc2_sqrt = (float)sqrt(1.0 - opt_p2);
+        const float coef = coef_s, decay = 1.0f - opt.lr * opt.wd;
+        for (int k = tid; k < n_i; k += TC_THREADS) {
+            const int i = i0 + k;
+            const float g = opt.grad[i] * coef;      // written by this CTA above
+            float pv = opt.params_rw[i] * decay;
+            const float mi = opt.m[i] + (1.0f - b1) * (g - opt.m[i]);
+            const float vi = fmaf(opt.v[i], b2, (1.0f - b2) * g * g);
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            pv = pv - step_size * (mi / denom);
+            opt.params_rw[i] = pv; opt.m[i] = mi; opt.v[i] = vi;
+        }
+    }
 }
 
 // grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x 16 block slices per
 // CTA; slice sl adds blocks sl, sl+16, ... (<= 10 independent loads in flight per thread for <= 160 blocks), and the
-// sixteen slice sums are combined in a fixed tree.  loss_out += block loss partials.
-constexpr int RED_SL = 16, RED_MAX = 10;
+// sixteen slice sums are combined in a fixed tree.  loss_out += block loss partials.  (Separate-kernel form of the fused
+// tail above: used when the gradient is needed on its own, e.g. for the allreduce of the sharded path.)
 __global__ void __launch_bounds__(64 * RED_SL)
 k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int stride, float *__restrict__ grad,
                      const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows) {
     __shared__ float part[RED_SL][64];
     const int p = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + p;
-    float s = 0.f;
-    if (i < P) {
-        for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
-            float v[RED_MAX];
-#pragma unroll
-            for (int u = 0; u < RED_MAX; ++u) {
-                const int bl = base + u * RED_SL;
-                v[u] = bl < nblocks ? __ldg(partials + (size_t)bl * stride + i) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < RED_MAX; ++u) s += v[u];
-        }
-    }
-    part[sl][p] = s;
+    part[sl][p] = i < P ? reduce_slice(partials, nblocks, stride, i, sl) : 0.f;
     __syncthreads();
     if (sl == 0 && i < P) {
         float t[RED_SL];
 #pragma unroll
         for (int u = 0; u < RED_SL; ++u) t[u] = part[u][p];
-#pragma unroll
-        for (int w = RED_SL / 2; w > 0; w >>= 1)
-#pragma unroll
-            for (int u = 0; u < w; ++u) t[u] += t[u + w];
-        grad[i] = t[0];
+        grad[i] = reduce_tree(t);
     }
     if (blockIdx.x == 0 && threadIdx.x < 3 && loss_out) {
         double t = 0.0;
@@ -699,33 +820,47 @@ int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim) {
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(batch);
-    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + 16;
+    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + 16;
 }
 
-int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
-                    const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
-                    float *grad, double *loss_out, float *ws, size_t ws_floats, void *stream) {
-    PRL_REQUIRE(params && states && actions && old_logp && adv && returns && grad && ws && b > 0, "prl_ppo_grad_tc: bad arguments");
+// shared launcher: gradient only (opt == nullptr: + separate reduction kernel) or fused optimiser step
+static int launch_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
+                     const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
+                     float *grad, double *loss_out, float *ws, size_t ws_floats, cudaStream_t st, const TcOptimizer *optp, const char *who) {
+    PRL_REQUIRE(params && states && actions && old_logp && adv && returns && grad && ws && b > 0, "%s: bad arguments", who);
     PRL_REQUIRE(prl_ppo_grad_tc_supported(is_continuous, obs_dim, action_dim),
-                "prl_ppo_grad_tc: only discrete policies with observ_dim <= %d and action_dim <= %d (got continuous=%d O=%d A=%d)", TC_MAX_O,
+                "%s: only discrete policies with observ_dim <= %d and action_dim <= %d (got continuous=%d O=%d A=%d)", who, TC_MAX_O,
                 TC_MAX_A, is_continuous, obs_dim, action_dim);
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
     const int grid = tc_grid(b);
     const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
-    PRL_REQUIRE(ws_floats >= 4 + (size_t)grid * pstride + (size_t)grid * 8 + 16, "prl_ppo_grad_tc: workspace too small");
-    PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "prl_ppo_grad_tc: workspace must be 16-byte aligned");
+    PRL_REQUIRE(ws_floats >= prl_update_tc_ws_floats(is_continuous, obs_dim, action_dim, b), "%s: workspace too small", who);
+    PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "%s: workspace must be 16-byte aligned", who);
     const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
     const size_t smem = tc_smem_bytes(L, NA);
-    PRL_REQUIRE(smem <= 227 * 1024, "prl_ppo_grad_tc: needs %zu B shared memory (> 227 KB)", smem);
-    cudaStream_t st = (cudaStream_t)stream;
-    // ws[0] = sticky status word (the caller zeroes the workspace once), then the per-block partial gradients and losses
+    PRL_REQUIRE(smem <= 227 * 1024, "%s: needs %zu B shared memory (> 227 KB)", who, smem);
+    // ws: [0] sticky status word, [1..2] grid-barrier counters (the caller zeroes the workspace once; the counters are
+    // re-zeroed before every fused launch), then per-CTA partial gradients, loss partials, squared-norm partials
     int *status = reinterpret_cast<int *>(ws);
     float *partials = ws + 4;
     double *loss_partials = reinterpret_cast<double *>(partials + (size_t)grid * pstride);
+    TcOptimizer opt{};
+    if (optp) {
+        opt = *optp;
+        opt.sync = reinterpret_cast<unsigned int *>(ws) + 1;
+        opt.sumsq = loss_partials + (size_t)grid * 4;
+        PRL_CUDA(cudaMemsetAsync(opt.sync, 0, 2 * sizeof(unsigned int), st));
+    }
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, TC_THREADS, smem, st>>>(params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
-                                             loss_partials, status);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;   // the fused tail spins on grid barriers: every CTA must be resident
+        attr[0].val.cooperative = optp ? 1 : 0;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
+                                    loss_partials, status, opt));
         return PRL_OK;
     };
     const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
@@ -734,14 +869,33 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
         long long c[32];
         PRL_CUDA(cudaStreamSynchronize(st));
         PRL_CUDA(cudaMemcpyFromSymbol(c, g_tc_clock, sizeof c));
-        fprintf(stderr, "[prl_ppo_grad_tc] CTA0 thread 0 cycles: setup %lld | tile 0: trunk fwd + stage F %lld, wait fwd MMA %lld, actor epilogue %lld, stage DZ %lld, "
+        fprintf(stderr, "[%s] CTA0 thread 0 cycles: setup %lld | tile 0: trunk fwd + stage F %lld, wait fwd MMA %lld, actor epilogue %lld, stage DZ %lld, "
                         "critic epilogue %lld, wait actor MMA + stage DZ %lld, wait critic MMA %lld, trunk bwd + stage %lld | all tiles %lld, final MMA wait %lld, "
-                        "readout %lld, tail %lld | kernel %lld\n",
+                        "readout %lld, tail %lld | kernel %lld\n", who,
                 c[1] - c[0], c[2] - c[1], c[4] - c[2], c[5] - c[4], c[6] - c[5], c[8] - c[6], c[9] - c[8], c[11] - c[9], c[12] - c[11], c[13] - c[1],
                 c[14] - c[13], c[15] - c[14], c[16] - c[15], c[16] - c[0]);
     }
-    k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
-    return check_launch("k_ppo_grad_tc");
+    if (!optp) k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
+    return check_launch(who);
+}
+
+int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
+                    const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
+                    float *grad, double *loss_out, float *ws, size_t ws_floats, void *stream) {
+    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
+                     ws, ws_floats, (cudaStream_t)stream, nullptr, "prl_ppo_grad_tc");
+}
+
+int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
+                    const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
+                    float *grad, double *loss_out, float *exp_avg, float *exp_avg_sq, int64_t *step_counter, float lr, float weight_decay,
+                    float max_norm, double *grad_norm_out, float *ws, size_t ws_floats, void *stream) {
+    PRL_REQUIRE(exp_avg && exp_avg_sq && step_counter, "prl_ppo_step_tc: bad optimiser arguments");
+    TcOptimizer opt{};
+    opt.params_rw = params; opt.grad = grad; opt.m = exp_avg; opt.v = exp_avg_sq; opt.clock = step_counter; opt.norm_out = grad_norm_out;
+    opt.lr = lr; opt.wd = weight_decay; opt.max_norm = max_norm; opt.loss_out = loss_out; opt.rows = (double)b;
+    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
+                     ws, ws_floats, (cudaStream_t)stream, &opt, "prl_ppo_step_tc");
 }
 
 /* ws[0]: 0 = every tensor-core phase of every call since the workspace was zeroed completed; 1 = an mbarrier wait timed

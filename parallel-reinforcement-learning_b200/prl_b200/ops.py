@@ -268,6 +268,16 @@ def ppo_grad_tc(params, is_continuous, O, A, states, actions, old_logp, adv, ret
          _ptr(ws, torch.float32), ws.numel(), _stream())
 
 
+def ppo_step_tc(params, is_continuous, O, A, states, actions, old_logp, adv, returns, policy_clip, inv_count, grad, loss_out, opt, ws):
+    """Gradient + clip_grad_norm_ + AdamW in one cooperative launch; `opt` is a prl_b200.optim.FusedAdamW."""
+    b = states.shape[0]
+    call("prl_ppo_step_tc", _ptr(params, torch.float32), int(is_continuous), O, A, _ptr(states, torch.float32),
+         _ptr(actions, torch.float32), _ptr(old_logp, torch.float32), _ptr(adv, torch.float32), _ptr(returns, torch.float32),
+         b, float(policy_clip), float(inv_count), _ptr(grad, torch.float32), _ptr(loss_out, torch.float64),
+         _ptr(opt.exp_avg, torch.float32), _ptr(opt.exp_avg_sq, torch.float32), _ptr(opt.step_dev, torch.int64), float(opt.lr),
+         float(opt.weight_decay), float(opt.max_norm), _ptr(opt.grad_norm, torch.float64), _ptr(ws, torch.float32), ws.numel(), _stream())
+
+
 def ppo_grad_tc_status(ws):
     st = C.c_int(0)
     call("prl_ppo_grad_tc_status", _ptr(ws, torch.float32), C.byref(st), _stream())

@@ -116,6 +116,28 @@ def test_learn_with_cuda_graph_epochs_is_bit_identical(api):
     assert out[0][2] == out[1][2] == out[0][3] == out[1][3] and out[0][2] >= 20
 
 
+def test_fused_optimizer_step_matches_separate_kernels(api):
+    """prl_ppo_step_tc (gradient + fixed-order reduction + clip + AdamW in one cooperative launch) against the three-kernel
+    sequence: same reduction order, so the gradient is bit-identical; the weights agree to float32 rounding of the norm."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    out = []
+    for fused in (False, True):
+        t.manual_seed(5)
+        ppo = P.PPO(is_continuous=False, observ_dim=4, action_dim=2, k_epochs=3, batch_size=256, mini_batch_size=1000)
+        ppo.show_progress = False
+        ppo.fused_optimizer = fused
+        ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=64), ppo=ppo, num_envs=256, steps=1)
+        ap.worker()
+        ppo.learn()
+        out.append((ppo.policy.flat.cpu().numpy(), ppo._grad.cpu().numpy(), ppo.optimizer.exp_avg.cpu().numpy(), ppo.optimizer.step_count,
+                    int(ppo.optimizer.step_dev[0].item()), ppo.last_losses.cpu().numpy()))
+    a, b = out
+    assert a[3] == b[3] == a[4] == b[4] and a[3] >= 6
+    np.testing.assert_allclose(b[0], a[0], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(b[5], a[5], rtol=1e-6)
+
+
 def test_learn_returns_early_below_batch_size(api, golden):
     g = golden("learn_discrete")
     ppo = make_ppo(api, g)
