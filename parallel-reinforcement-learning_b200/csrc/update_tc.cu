@@ -79,9 +79,17 @@ __device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3,
     c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
     return c0;
 }
-__device__ __forceinline__ void colsum16(const float (&v)[TC_W], float (&acc)[2]) {
-    acc[0] += colsum8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-    acc[1] += colsum8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+// column sums of the thread's two groups, accumulated into the warp's 16-float slot of the shared accumulator array
+// (slot[8 g + f(lane)] += total; one of the four lanes holding a feature does the update)
+__device__ __forceinline__ void colsum16(const float (&v)[TC_W], float *slot) {
+    const float c0 = colsum8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    const float c1 = colsum8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+    const int lane = threadIdx.x & 31;
+    if ((lane & 3) == 0) {
+        const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        slot[f] += c0;
+        slot[8 + f] += c1;
+    }
 }
 
 // GroupNorm on the thread's two groups: z -> zhat in place, rstd per group
@@ -366,14 +374,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         }
     } else {
         // =============================================================================== compute warps
-        // per-warp column-sum accumulators for this thread's two groups (feature f(lane) of each)
-        float q_g0[2] = {0.f, 0.f}, q_b0[2] = {0.f, 0.f};
-        float q_g[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, q_b[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-        float q_w2[2][NA][2], q_b2[2][NA];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int a = 0; a < NA; ++a) { q_w2[h][a][0] = q_w2[h][a][1] = 0.f; q_b2[h][a] = 0.f; }
+        // column-sum accumulators live in shared memory: s_red[rq][quantity][64 features]; this warp owns features j0..j0+15
+        // of row quarter rq.  Quantities: 0 dgamma0, 1 dbeta0, then per head: dgamma, dbeta, dW2[a] (a < out).
+        const int NQ = tc_num_q(L);
+        float *acc = s_red + (size_t)rq * NQ * HID + j0;
+        const int qh[2] = {2, 2 + 2 + L.head[0].out};
+        for (int i = lane; i < NQ * TC_W; i += 32) acc[(i / TC_W) * HID + (i % TC_W)] = 0.f;
+        if (q == 0 && lane < 2 * TC_MAX_A) (&b2s[rq][0][0])[lane] = 0.f;
+        __syncwarp();
 
         // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
         constexpr int XR = 8;   // observation values kept in registers (observ_dim > 8 reads the rest on demand)
@@ -402,8 +410,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             const int act = live ? (int)__ldg(actions + row) : 0;
 
             // ================= trunk forward (CUDA cores): z0 = W0 x, GroupNorm, SiLU -> F pieces, X pieces
-            float zh0[TC_W], rs0[2];
-            {
+            auto trunk_pre = [&](float (&zh0)[TC_W], float (&rs0)[2]) {
 #pragma unroll
                 for (int j = 0; j < TC_W; ++j) zh0[j] = 0.f;
 #pragma unroll
@@ -423,6 +430,10 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(xi, w[j], zh0[j]);
                 }
                 gn_normalize16(zh0, rs0);
+            };
+            {
+                float zh0[TC_W], rs0[2];
+                trunk_pre(zh0, rs0);
                 float f[TC_W], g0w[TC_W], g0b[TC_W];
                 load16(s_g0w + j0, g0w);
                 load16(s_g0b + j0, g0b);
@@ -544,8 +555,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                         float t[TC_W];
 #pragma unroll
                         for (int j = 0; j < TC_W; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
-                        colsum16(t, q_w2[h][a]);
-                        if (q == 0) q_b2[h][a] += warp_sum(dout[a]);
+                        colsum16(t, acc + (qh[h] + 2 + a) * HID);
+                        if (q == 0) {
+                            const float sb = warp_sum(dout[a]);
+                            if (lane == 0) b2s[rq][h][a] += sb;
+                        }
                     }
                 }
                 // ---- dy (in place of sg), GroupNorm-affine gradients, GroupNorm backward -> dz
@@ -562,8 +576,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     float t[TC_W];
 #pragma unroll
                     for (int j = 0; j < TC_W; ++j) t[j] = sg[j] * zhat[j];
-                    colsum16(t, q_g[h]);
-                    colsum16(sg, q_b[h]);
+                    colsum16(t, acc + qh[h] * HID);
+                    colsum16(sg, acc + (qh[h] + 1) * HID);
                 }
                 gn_backward16(sg, zhat, rstd, gw);   // sg now holds dz
                 if (it == 0) TC_STAMP(5 + 3 * h);
@@ -576,7 +590,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 
             // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
             {
-                float df[TC_W], g0w[TC_W], g0b[TC_W];
+                float df[TC_W], g0w[TC_W], g0b[TC_W], zh0[TC_W], rs0[2];
+                trunk_pre(zh0, rs0);   // recomputed (cheap) rather than kept in registers across the head phases
                 load16(s_g0w + j0, g0w);
                 load16(s_g0b + j0, g0b);
                 mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final; DZ free again
@@ -593,8 +608,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     float t[TC_W];
 #pragma unroll
                     for (int j = 0; j < TC_W; ++j) t[j] = df[j] * zh0[j];
-                    colsum16(t, q_g0);
-                    colsum16(df, q_b0);
+                    colsum16(t, acc);
+                    colsum16(df, acc + HID);
                 }
                 gn_backward16(df, zh0, rs0, g0w);
                 store_pieces16(sDZ, r, q, df);
@@ -640,29 +655,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 part[L.w0 + idx] = (it > 0) ? scratch[j * 17 + i] + scratch[(64 + j) * 17 + i] : 0.f;
             }
         }
-        // column-sum accumulators: lanes with (lane & 3) == 0 publish feature 16q + 8g + f(lane); combine the four row quarters
+        // column-sum accumulators (already in s_red / b2s): combine the four row quarters
         {
-            bar_compute();
-            const int NQ = tc_num_q(L);
-            float *r4 = s_red + (size_t)rq * NQ * HID;
-            const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if ((lane & 3) == 0) {
-                int qq = 0;
-                auto put = [&](const float (&sv)[2]) { r4[qq * HID + j0 + f] = sv[0]; r4[qq * HID + j0 + 8 + f] = sv[1]; ++qq; };
-                put(q_g0); put(q_b0);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    put(q_g[h]); put(q_b[h]);
-#pragma unroll
-                    for (int a = 0; a < NA; ++a)
-                        if (a < L.head[h].out) put(q_w2[h][a]);
-                }
-            }
-            if (q == 0 && lane == 0)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int a = 0; a < NA; ++a) b2s[rq][h][a] = q_b2[h][a];
             bar_compute();
             for (int idx = tid; idx < NQ * HID; idx += TC_COMPUTE) {
                 const int qq = idx / HID, j = idx - qq * HID;
