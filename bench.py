@@ -189,8 +189,8 @@ def run_b200(args):
     from prl_b200 import _lib
     from prl_b200 import dist as pdist
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]   # keep stdout to the one JSON line (at these levels NCCL prints a version banner there)
     comm = pdist.init_from_env()
     rank = comm.rank if comm else 0
     world = comm.world_size if comm else 1
@@ -204,7 +204,10 @@ def run_b200(args):
     ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=1e-3, k_epochs=args.k_epochs, batch_size=1024,
               mini_batch_size=args.mini_batch * world)
     ppo.show_progress = False
-    ppo.use_cuda_graph = True   # one captured epoch replayed k_epochs times (single process; see PPO.learn)
+    ppo.use_cuda_graph = True   # one captured epoch replayed k_epochs times (see PPO.learn)
+    ppo.graph_collectives = os.environ.get("PRL_GRAPH_COLLECTIVES", "1") == "1"   # NCCL allreduce captured in the graph too
+    # sharded runs: gradient exchange over NVLink peer memory inside the step kernel (0 = NCCL allreduce between grad and AdamW)
+    ppo.peer_exchange = os.environ.get("PRL_PEER_EXCHANGE", "1") == "1"
     ppo._seed += rank  # different action noise per shard
     t.manual_seed(1234 + rank)  # different env reset stream per shard
     ap = AsyncPPO(env=prl_b200.make("CartPole-v1", max_episode_steps=T), ppo=ppo, num_envs=E, steps=1)
@@ -271,14 +274,17 @@ def run_b200(args):
         per[name] = {"calls": len(evs), "ms": sum(a.elapsed_time(b) for a, b in evs)}
     pk = peaks()
     roof = None
-    gk = "prl_ppo_grad_tc" if "prl_ppo_grad_tc" in per else "prl_ppo_grad"
-    if gk in per:
+    gk = next((k_ for k_ in ("prl_ppo_step_tc_p2p", "prl_ppo_step_tc", "prl_ppo_grad_tc", "prl_ppo_grad") if k_ in per), None)
+    kernel_names = {
+        "prl_ppo_step_tc_p2p": "k_ppo_grad_tc (prl_ppo_step_tc_p2p: forward + loss + backward on tcgen05 bf16x3 MMAs, then gradient exchange over NVLink peer memory + clip + AdamW in the same cooperative launch)",
+        "prl_ppo_step_tc": "k_ppo_grad_tc (prl_ppo_step_tc: forward + loss + backward on tcgen05 bf16x3 MMAs, then reduce + clip + AdamW in the same cooperative launch)",
+        "prl_ppo_grad_tc": "k_ppo_grad_tc (prl_ppo_grad_tc: fused forward + loss + backward, tcgen05 bf16x3 MMAs + CUDA-core epilogues)",
+        "prl_ppo_grad": "k_ppo_grad (prl_ppo_grad: fused forward + loss + backward, fp32 FMA path)"}
+    if gk is not None:
         g = per[gk]
         rows_epochs = n_prof / world * args.k_epochs           # sample-epochs this rank pushed through the update kernel
         tf = rows_epochs * FLOPS_PER_SAMPLE_EPOCH / (g["ms"] * 1e-3) / 1e12
-        roof = {"kernel": ("k_ppo_grad_tc (prl_ppo_grad_tc: fused forward + loss + backward, tcgen05 bf16x3 MMAs + CUDA-core epilogues)"
-                           if gk == "prl_ppo_grad_tc" else "k_ppo_grad (prl_ppo_grad: fused forward + loss + backward, fp32 FMA path)"),
-                "bound": "tensor", "achieved": tf,
+        roof = {"kernel": kernel_names[gk], "bound": "tensor", "achieved": tf,
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"], "traffic": None,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
@@ -316,7 +322,7 @@ def run_b200(args):
         out["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"1 step of {args.cpu_sample_envs} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
                                          f"{cs} env-steps in {csec:.1f} s"}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def hbm_microbench(pk, E=65536, T=128):
@@ -389,6 +395,10 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        import torch.distributed as td
+
+        if td.is_available() and td.is_initialized():
+            td.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -164,6 +164,24 @@ int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_di
                     float policy_clip, float inv_count, float *grad, double *loss_out, float *exp_avg,
                     float *exp_avg_sq, int64_t *step_counter, float lr, float weight_decay, float max_norm,
                     double *grad_norm_out, float *ws, size_t ws_floats, void *stream);
+/* Sharded form of prl_ppo_step_tc: the gradient allreduce happens INSIDE the kernel over NVLink peer memory.  Every rank
+ * owns an exchange buffer (prl_p2p_alloc of prl_p2p_exchange_bytes; shared with the other ranks of the node through CUDA
+ * IPC handles: prl_p2p_get_handle / prl_p2p_open_handle); peer_bufs is a DEVICE array of `world` pointers to the ranks'
+ * buffers (own one at [rank]).  Each rank writes its locally reduced gradient into its buffer, raises a flag on every
+ * peer, and sums all ranks' buffers in rank order (bit-identical on every rank) before clip + AdamW.  b may be 0 (a rank
+ * without rows in this minibatch still takes part).  Status word 3 = a peer never signalled. */
+int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
+                        const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
+                        float policy_clip, float inv_count, float *grad, double *loss_out, float *exp_avg,
+                        float *exp_avg_sq, int64_t *step_counter, float lr, float weight_decay, float max_norm,
+                        double *grad_norm_out, void *const *peer_bufs, int rank, int world, float *ws, size_t ws_floats,
+                        void *stream);
+size_t prl_p2p_exchange_bytes(int is_continuous, int obs_dim, int action_dim, int world);
+int prl_p2p_alloc(size_t bytes, void **ptr);
+int prl_p2p_free(void *ptr);
+int prl_p2p_get_handle(void *ptr, unsigned char *handle64);
+int prl_p2p_open_handle(const unsigned char *handle64, void **ptr);
+int prl_p2p_close_handle(void *ptr);
 /* nn.utils.clip_grad_norm_(params, max_norm) + AdamW.step (PPO.py:250-252; torch defaults betas (0.9,0.999),
  * eps 1e-8, weight_decay 0.01).  step = 1-based optimiser step count. max_norm <= 0 disables clipping. */
 int prl_adamw_step(float *params, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, int64_t step,

@@ -86,7 +86,10 @@ class PPO:
         self._rows = None
         # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies), "fp32" = CUDA-core
         # FMA kernel (csrc/update_ppo.cu; every configuration).  Same math and tolerances, two members of one family.
+        self.peer_exchange = True     # sharded tensor path: gradient exchange over peer memory inside the step kernel
+        self._xch = None
         self.fused_optimizer = True   # tensor path, single process: one launch per optimiser step (prl_ppo_step_tc)
+        self.graph_collectives = False  # also capture the per-minibatch gradient allreduce (NCCL) in the epoch graph
         self.use_cuda_graph = False   # capture each epoch of learn() in a CUDA graph (single process, >= 16 optimiser steps)
         self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
 
@@ -132,14 +135,23 @@ class PPO:
     # ------------------------------------------------------------------------------------------------ learn
     @t.no_grad()
     def learn(self):
-        if len(self.memory.states) < self.batch_size:
-            return
+        comm = pdist.active()
+        if comm is None:
+            if len(self.memory.states) < self.batch_size:   # PPO.py:123-124
+                return
+        else:
+            # sharded: the decision has to be the same on every rank (learn() is collective) - batch_size counts the rows of
+            # all shards together
+            n_all = comm.allgather_int(len(self.memory.states))
+            if sum(n_all) < self.batch_size:
+                return
+            if min(n_all) == 0:
+                raise RuntimeError(f"sharded learn(): a rank holds no transitions (rows per rank: {n_all})")
         O, A, cont = self.observ_dim, self.action_dim, self.is_continuous
         AW = A if cont else 1
         states, actions, rewards, dones = self.memory.device_view(O, AW, self.device)
         N = states.shape[0]
         mb = int(self.mini_batch_size)
-        comm = pdist.active()
 
         # per-row scratch, allocated once at the store's capacity and reused by every learn() (no allocator traffic)
         cap = max(self.memory._dev_cap, N)
@@ -172,7 +184,7 @@ class PPO:
         # minibatch schedule: sequential chunks of the flat env-major buffer, same order every epoch (PPO.py:202-211).
         # Sharded: global minibatch k = union of every rank's k-th local chunk.
         if comm is not None:
-            mb_local, n_mb, counts = pdist.minibatch_schedule(comm.allgather_int(N), mb)
+            mb_local, n_mb, counts = pdist.minibatch_schedule(n_all, mb)
         else:
             mb_local, n_mb = mb, -(-N // mb)
             counts = [min(N - k * mb, mb) for k in range(n_mb)]
@@ -187,9 +199,19 @@ class PPO:
         steps = self.k_epochs * n_mb
 
         fused = use_tc and comm is None and self.fused_optimizer   # gradient + clip + AdamW in one cooperative launch
+        # sharded: the same single launch, with the gradient exchange over NVLink peer memory inside it (no NCCL per step)
+        p2p = use_tc and comm is not None and self.fused_optimizer and self.peer_exchange
+        if p2p and self._xch is None:
+            self._xch = pdist.PeerExchange(comm, cont, O, A)
 
         def minibatch_step(k, loss_slot):
             lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
+            if p2p:
+                rows = (states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi], returns[lo:hi]) if hi > lo else (None,) * 5
+                ops.ppo_step_tc_p2p(self.policy.flat, cont, O, A, *rows, self.policy_clip, 1.0 / counts[k], self._grad, loss_slot,
+                                    self.optimizer, self._ws, self._xch)
+                self.optimizer.step_count += 1
+                return hi - lo
             if fused:
                 ops.ppo_step_tc(self.policy.flat, cont, O, A, states[lo:hi], actions[lo:hi], old_logp[lo:hi], adv[lo:hi],
                                 returns[lo:hi], self.policy_clip, 1.0 / counts[k], self._grad, loss_slot, self.optimizer, self._ws)
@@ -205,7 +227,8 @@ class PPO:
             self.optimizer.step(self._grad)
             return hi - lo
 
-        use_graph = self.use_cuda_graph and comm is None and not self.report_loss and steps >= 16
+        # (sharded runs capture the NCCL allreduce inside the graph as well when graph_collectives is set)
+        use_graph = self.use_cuda_graph and (comm is None or self.graph_collectives or p2p) and not self.report_loss and steps >= 16
         pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
         if use_graph:
             # one epoch = n_mb launch triples with fixed pointers: capture once, replay k_epochs times (no host work between
@@ -244,8 +267,11 @@ class PPO:
                     step += 1
         if pbar is not None:
             pbar.close()
-        if use_tc and ops.ppo_grad_tc_status(self._ws) != 0:
-            raise RuntimeError("tensor-core update: an MMA phase never completed (mbarrier timeout)")
+        status = ops.ppo_grad_tc_status(self._ws) if use_tc else 0
+        if status != 0:
+            raise RuntimeError("tensor-core update failed: " + {1: "an MMA phase never completed (mbarrier timeout)",
+                                                                  2: "grid barrier timed out",
+                                                                  3: "a peer rank never signalled its gradient"}.get(status, f"status {status}"))
         self.policy_old.flat.copy_(self.policy.flat)  # PPO.py:258-260
 
     # ------------------------------------------------------------------------------------------------ checkpoints

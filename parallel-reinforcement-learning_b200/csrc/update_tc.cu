@@ -19,6 +19,7 @@
 // and the narrow column sums (GroupNorm affine and output-layer gradients), done as warp butterfly reductions into
 // per-warp register accumulators that are combined once at the end.
 #include <stdlib.h>
+#include <string.h>
 
 #include "policy.cuh"
 #include "umma.cuh"
@@ -210,7 +211,26 @@ struct TcOptimizer {
     float lr, wd, max_norm;
     double *loss_out;                         // 4 doubles, accumulated
     double rows;
+    // sharded runs: the gradient exchange happens inside this kernel over NVLink peer memory instead of an NCCL allreduce.
+    // peers[r] = base of rank r's exchange buffer {G[2][gstride] float (double-buffered by step parity), flags[world] u32}
+    float *const *peers;
+    int rank, world, gstride;
 };
+
+// one-shot cross-GPU exchange helpers (system-scope release / acquire on the flag words in peer memory)
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // grid-wide barrier for a grid whose CTAs are all resident (cooperative launch): bounded spin, false on time-out
 __device__ __forceinline__ bool grid_barrier(unsigned int *counter, unsigned int nblocks) {
@@ -703,6 +723,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     float *sl_part = reinterpret_cast<float *>(smem_raw);             // [RED_SL][RC] slice sums
     double *sq = reinterpret_cast<double *>(smem_raw + 8192);         // [RC] squared gradients
     double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slice
+    const bool sharded = opt.world > 1;
+    // destination of the locally reduced gradient: the final gradient buffer, or (sharded) my peer-visible exchange buffer
+    float *gdst = sharded ? opt.peers[opt.rank] + (int)(opt_step & 1) * opt.gstride : opt.grad;
     for (int c0 = 0; c0 < n_i; c0 += RC) {
         const int nc = min(RC, n_i - c0);
         for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
@@ -715,22 +738,60 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 #pragma unroll
             for (int u = 0; u < RED_SL; ++u) t16[u] = sl_part[u * RC + tid];
             const float gi = reduce_tree(t16);
-            opt.grad[i0 + c0 + tid] = gi;
+            gdst[i0 + c0 + tid] = gi;
             sq[tid] = (double)gi * gi;
         }
         __syncthreads();
         if (tid == 0)
             for (int k = 0; k < nc; ++k) ssum += sq[k];
     }
-    if (tid == 0) {
-        opt.sumsq[blockIdx.x] = ssum;
-        if (blockIdx.x == 0) {   // losses of the whole launch (same bookkeeping as k_reduce_partials_tc); the other CTAs'
-            // loss partials are visible: they were written before the first grid barrier
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-            for (int bl = 0; bl < nb; ++bl) { a0 += loss_partials[bl * 4]; a1 += loss_partials[bl * 4 + 1]; a2 += loss_partials[bl * 4 + 2]; }
-            if (opt.loss_out) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
+    if (tid == 0 && blockIdx.x == 0) {   // losses of the whole launch (same bookkeeping as k_reduce_partials_tc); the other
+        // CTAs' loss partials are visible: they were written before the first grid barrier
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int bl = 0; bl < nb; ++bl) { a0 += loss_partials[bl * 4]; a1 += loss_partials[bl * 4 + 1]; a2 += loss_partials[bl * 4 + 2]; }
+        if (opt.loss_out) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
+    }
+    if (sharded) {
+        // ---- gradient exchange over peer memory: my reduced slice sits in my exchange buffer; once every CTA has written
+        // its slice, CTA 0 raises my flag on every rank; then each CTA sums the W ranks' buffers over its slice in rank
+        // order (identical result on every rank) - the allreduce, without leaving the kernel
+        if (!grid_barrier(opt.sync + 2, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+        const unsigned int epoch = (unsigned int)opt_step;
+        const int flag_off = 2 * opt.gstride;   // in 4-byte words
+        if (blockIdx.x == 0 && tid < opt.world) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<unsigned int *>(opt.peers[tid]) + flag_off + opt.rank, epoch);
+        }
+        __shared__ int peers_ok;
+        if (tid == 0) {
+            const unsigned int *myflags = reinterpret_cast<const unsigned int *>(opt.peers[opt.rank]) + flag_off;
+            int ok = 1;
+            for (int rr = 0; rr < opt.world && ok; ++rr) {
+                ok = 0;
+                for (int itp = 0; itp < (1 << 24); ++itp)
+                    if ((int)(ld_acquire_sys(myflags + rr) - epoch) >= 0) { ok = 1; break; }
+            }
+            peers_ok = ok;
+        }
+        __syncthreads();
+        if (!peers_ok) { if (tid == 0) atomicExch(status, 3); return; }
+        ssum = 0.0;
+        const int goff = (int)(opt_step & 1) * opt.gstride;
+        for (int c0 = 0; c0 < n_i; c0 += RC) {
+            const int nc = min(RC, n_i - c0);
+            if (tid < nc) {
+                float g = 0.f;
+                for (int rr = 0; rr < opt.world; ++rr) g += ld_relaxed_sys(opt.peers[rr] + goff + i0 + c0 + tid);
+                opt.grad[i0 + c0 + tid] = g;
+                sq[tid] = (double)g * g;
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int k = 0; k < nc; ++k) ssum += sq[k];
+            __syncthreads();
         }
     }
+    if (tid == 0) opt.sumsq[blockIdx.x] = ssum;
     if (!grid_barrier(opt.sync + 1, nb)) { if (tid == 0) atomicExch(status, 2); return; }
     __shared__ float coef_s;
     if (warp == 0) {
@@ -821,7 +882,8 @@ size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, i
 static int launch_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
                      const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
                      float *grad, double *loss_out, float *ws, size_t ws_floats, cudaStream_t st, const TcOptimizer *optp, const char *who) {
-    PRL_REQUIRE(params && states && actions && old_logp && adv && returns && grad && ws && b > 0, "%s: bad arguments", who);
+    PRL_REQUIRE(params && grad && ws && b >= 0 && (b > 0 || (optp && optp->world > 1)), "%s: bad arguments", who);
+    PRL_REQUIRE(b == 0 || (states && actions && old_logp && adv && returns), "%s: null row pointer", who);
     PRL_REQUIRE(prl_ppo_grad_tc_supported(is_continuous, obs_dim, action_dim),
                 "%s: only discrete policies with observ_dim <= %d and action_dim <= %d (got continuous=%d O=%d A=%d)", who, TC_MAX_O,
                 TC_MAX_A, is_continuous, obs_dim, action_dim);
@@ -843,7 +905,7 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
         opt = *optp;
         opt.sync = reinterpret_cast<unsigned int *>(ws) + 1;
         opt.sumsq = loss_partials + (size_t)grid * 4;
-        PRL_CUDA(cudaMemsetAsync(opt.sync, 0, 2 * sizeof(unsigned int), st));
+        PRL_CUDA(cudaMemsetAsync(opt.sync, 0, 3 * sizeof(unsigned int), st));
     }
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -890,6 +952,54 @@ int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_di
     opt.lr = lr; opt.wd = weight_decay; opt.max_norm = max_norm; opt.loss_out = loss_out; opt.rows = (double)b;
     return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
                      ws, ws_floats, (cudaStream_t)stream, &opt, "prl_ppo_step_tc");
+}
+
+int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
+                        const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
+                        float *grad, double *loss_out, float *exp_avg, float *exp_avg_sq, int64_t *step_counter, float lr,
+                        float weight_decay, float max_norm, double *grad_norm_out, void *const *peer_bufs, int rank, int world, float *ws,
+                        size_t ws_floats, void *stream) {
+    PRL_REQUIRE(exp_avg && exp_avg_sq && step_counter && peer_bufs && world >= 1 && world <= 64 && rank >= 0 && rank < world,
+                "prl_ppo_step_tc_p2p: bad arguments");
+    const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
+    TcOptimizer opt{};
+    opt.params_rw = params; opt.grad = grad; opt.m = exp_avg; opt.v = exp_avg_sq; opt.clock = step_counter; opt.norm_out = grad_norm_out;
+    opt.lr = lr; opt.wd = weight_decay; opt.max_norm = max_norm; opt.loss_out = loss_out; opt.rows = (double)b;
+    opt.peers = reinterpret_cast<float *const *>(peer_bufs); opt.rank = rank; opt.world = world; opt.gstride = (L.total + 3) & ~3;
+    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
+                     ws, ws_floats, (cudaStream_t)stream, &opt, "prl_ppo_step_tc_p2p");
+}
+
+size_t prl_p2p_exchange_bytes(int is_continuous, int obs_dim, int action_dim, int world) {
+    const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
+    return ((size_t)2 * ((L.total + 3) & ~3) + (size_t)world) * 4 + 256;
+}
+int prl_p2p_alloc(size_t bytes, void **ptr) {
+    PRL_REQUIRE(ptr && bytes > 0, "prl_p2p_alloc: bad arguments");
+    PRL_CUDA(cudaMalloc(ptr, bytes));
+    PRL_CUDA(cudaMemset(*ptr, 0, bytes));
+    return PRL_OK;
+}
+int prl_p2p_free(void *ptr) {
+    PRL_CUDA(cudaFree(ptr));
+    return PRL_OK;
+}
+int prl_p2p_get_handle(void *ptr, unsigned char *handle64) {
+    PRL_REQUIRE(ptr && handle64, "prl_p2p_get_handle: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PRL_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), ptr));
+    return PRL_OK;
+}
+int prl_p2p_open_handle(const unsigned char *handle64, void **ptr) {
+    PRL_REQUIRE(ptr && handle64, "prl_p2p_open_handle: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    PRL_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PRL_OK;
+}
+int prl_p2p_close_handle(void *ptr) {
+    PRL_CUDA(cudaIpcCloseMemHandle(ptr));
+    return PRL_OK;
 }
 
 /* ws[0]: 0 = every tensor-core phase of every call since the workspace was zeroed completed; 1 = an mbarrier wait timed

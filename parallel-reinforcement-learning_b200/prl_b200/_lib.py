@@ -54,6 +54,14 @@ PROTOTYPES = {
     "prl_ppo_grad_tc_status": (_i32, [_vp, _vp, _vp]),
     "prl_ppo_step_tc": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32,
                                _vp, _vp, _sz, _vp]),
+    "prl_ppo_step_tc_p2p": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _f32, _f32,
+                                   _f32, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
+    "prl_p2p_exchange_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "prl_p2p_alloc": (_i32, [_sz, C.POINTER(_vp)]),
+    "prl_p2p_free": (_i32, [_vp]),
+    "prl_p2p_get_handle": (_i32, [_vp, C.c_char_p]),
+    "prl_p2p_open_handle": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "prl_p2p_close_handle": (_i32, [_vp]),
     "prl_adamw_step_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp]),
     "prl_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _vp, _vp]),
     "prl_rnd_intrinsic": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f32, _vp, _vp, _vp]),
@@ -98,7 +106,7 @@ KERNELS_PER_CALL = {
     "prl_test_sincos": 1, "prl_test_pow2": 1, "prl_test_philox": 1, "prl_test_umma": 1, "prl_env_reset": 1, "prl_env_set_state": 1,
     "prl_env_get_state": 1, "prl_env_step": 1, "prl_compact_indices": 2, "prl_gather_rows": 1, "prl_mask_update": 1,
     "prl_buffer_append": 1, "prl_buffer_transfer": 7, "prl_policy_act": 1, "prl_policy_evaluate": 1, "prl_rollout": 1,
-    "prl_gae": 1, "prl_gae_columns": 1, "prl_adv_normalize": 1, "prl_ppo_grad": 2, "prl_ppo_grad_tc": 2, "prl_ppo_step_tc": 1, "prl_adamw_step": 1, "prl_adamw_step_dev": 1,
+    "prl_gae": 1, "prl_gae_columns": 1, "prl_adv_normalize": 1, "prl_ppo_grad": 2, "prl_ppo_grad_tc": 2, "prl_ppo_step_tc": 1, "prl_ppo_step_tc_p2p": 1, "prl_adamw_step": 1, "prl_adamw_step_dev": 1,
     "prl_rnd_intrinsic": 1, "prl_rnd_grad": 2,
 }
 CALL_COUNTS: dict[str, int] = {}

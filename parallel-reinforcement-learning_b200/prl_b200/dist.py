@@ -83,3 +83,34 @@ def activate(comm: Comm | None):
 
 def active() -> Comm | None:
     return _ACTIVE
+
+
+class PeerExchange:
+    """Per-rank gradient exchange buffers shared across the GPUs of one node through CUDA IPC (NVLink / NVSwitch peer
+    memory): what prl_ppo_step_tc_p2p sums over instead of calling an NCCL allreduce.  `table` is a device int64 tensor
+    holding the `world_size` buffer addresses as seen from this process (own buffer at [rank])."""
+
+    def __init__(self, comm: Comm, is_continuous: bool, observ_dim: int, action_dim: int):
+        import ctypes as C
+
+        from . import _lib
+
+        self.rank, self.world_size = comm.rank, comm.world_size
+        nbytes = int(_lib.fn("prl_p2p_exchange_bytes")(int(is_continuous), observ_dim, action_dim, self.world_size))
+        own = C.c_void_p()
+        _lib.call("prl_p2p_alloc", nbytes, C.byref(own))
+        handle = C.create_string_buffer(64)
+        _lib.call("prl_p2p_get_handle", own, handle)
+        handles = [None] * self.world_size
+        td.all_gather_object(handles, bytes(handle.raw), group=comm.group)
+        self._own, self._opened, ptrs = own, [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(own.value)
+            else:
+                p = C.c_void_p()
+                _lib.call("prl_p2p_open_handle", C.create_string_buffer(h, 64), C.byref(p))
+                self._opened.append(p)
+                ptrs.append(p.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        comm.barrier()   # every rank has mapped every buffer before anybody signals through them

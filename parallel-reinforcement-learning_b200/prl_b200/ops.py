@@ -278,6 +278,16 @@ def ppo_step_tc(params, is_continuous, O, A, states, actions, old_logp, adv, ret
          float(opt.weight_decay), float(opt.max_norm), _ptr(opt.grad_norm, torch.float64), _ptr(ws, torch.float32), ws.numel(), _stream())
 
 
+def ppo_step_tc_p2p(params, is_continuous, O, A, states, actions, old_logp, adv, returns, policy_clip, inv_count, grad, loss_out, opt, ws, xch):
+    """Sharded prl_ppo_step_tc: gradient exchange over peer memory inside the kernel (`xch`: prl_b200.dist.PeerExchange)."""
+    b = states.shape[0] if states is not None else 0
+    call("prl_ppo_step_tc_p2p", _ptr(params, torch.float32), int(is_continuous), O, A, _ptr(states), _ptr(actions), _ptr(old_logp),
+         _ptr(adv), _ptr(returns), b, float(policy_clip), float(inv_count), _ptr(grad, torch.float32), _ptr(loss_out, torch.float64),
+         _ptr(opt.exp_avg, torch.float32), _ptr(opt.exp_avg_sq, torch.float32), _ptr(opt.step_dev, torch.int64), float(opt.lr),
+         float(opt.weight_decay), float(opt.max_norm), _ptr(opt.grad_norm, torch.float64), _ptr(xch.table, torch.int64), xch.rank,
+         xch.world_size, _ptr(ws, torch.float32), ws.numel(), _stream())
+
+
 def ppo_grad_tc_status(ws):
     st = C.c_int(0)
     call("prl_ppo_grad_tc_status", _ptr(ws, torch.float32), C.byref(st), _stream())

@@ -1,0 +1,45 @@
+"""Two-rank GPU worker (launched by tests/test_gpu_multi.py through torch.distributed.run): the sharded PPO update with
+the in-kernel peer-memory gradient exchange (prl_ppo_step_tc_p2p) must leave every rank with the same weights as the
+NCCL-allreduce path, eager and as a CUDA graph.  Writes `ok` to <out>/rank<r> on success."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "..", "parallel-reinforcement-learning_b200"))
+import torch as t
+
+from prl_b200 import dist, make
+from PPO import PPO
+from AsyncTools.AsyncPPO import AsyncPPO
+
+out = sys.argv[1]
+comm = dist.init_from_env()
+rank = comm.rank
+env = make("CartPole-v1")
+
+
+def run(peer_exchange, graph, envs):
+    t.manual_seed(1234)
+    ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=3e-4, k_epochs=3, mini_batch_size=1024, batch_size=256, use_RND=False)
+    ppo.update_path, ppo.peer_exchange, ppo.use_cuda_graph, ppo.graph_collectives, ppo.show_progress = "tensor", peer_exchange, graph, graph, False
+    t.manual_seed(99 + rank)   # a different env reset stream per shard
+    a = AsyncPPO(env=env, ppo=ppo, num_envs=envs, steps=10**9)
+    for _ in range(2):   # two rollouts + updates: the second one exercises the persistent exchange flags / step parity
+        a.worker()
+        ppo.learn()
+    t.cuda.synchronize()
+    return ppo.policy.flat.clone(), None
+
+
+# rank 1 gets fewer envs, so its row count differs and the last minibatches have no rows on it (b == 0 launches)
+envs = 192 if rank == 0 else 40
+ref, _ = run(False, False, envs)
+for graph in (False, True):
+    got, st = run(True, graph, envs)
+    d = (got - ref).abs().max().item()
+    # rank-order summation of two addends is commutative, so the exchange is bit-identical to NCCL's sum
+    assert d == 0.0, f"rank {rank} graph={graph}: peer-exchange weights differ from NCCL path by {d}"
+    both = [t.empty_like(got) for _ in range(2)]
+    t.distributed.all_gather(both, got)
+    assert t.equal(both[0], both[1]), "ranks diverged"
+open(os.path.join(out, f"rank{rank}"), "w").write("ok")
+t.distributed.destroy_process_group()
