@@ -205,7 +205,7 @@ __device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[TC_W]) {
 struct TcOptimizer {
     float *params_rw, *grad, *m, *v;          // params_rw == nullptr: gradient only (the reduction runs as a separate kernel)
     int64_t *clock;                           // {int64 step, double beta1^step, double beta2^step}
-    unsigned int *sync;                       // two zeroed counters (grid barriers)
+    unsigned int *sync;                       // {arrival count, generation} of the grid barrier
     double *sumsq;                            // [grid] squared-norm partials
     double *norm_out;
     float lr, wd, max_norm;
@@ -232,18 +232,27 @@ __device__ __forceinline__ float ld_relaxed_sys(const float *p) {
     return v;
 }
 
-// grid-wide barrier for a grid whose CTAs are all resident (cooperative launch): bounded spin, false on time-out
-__device__ __forceinline__ bool grid_barrier(unsigned int *counter, unsigned int nblocks) {
+// grid-wide barrier for a grid whose CTAs are all resident (cooperative launch): bounded spin, false on time-out.
+// bar = {arrival count, generation}, both zero once (workspace allocation); the last CTA to arrive resets the count and
+// advances the generation, so the same pair serves every barrier of every launch with no host-side reset in between.
+__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks) {
     __syncthreads();
     __shared__ int ok_s;
     if (threadIdx.x == 0) {
+        unsigned int gen, cur;
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");   // cannot advance before this CTA arrives
         __threadfence();
-        atomicAdd(counter, 1u);
-        int ok = 0;
-        for (int it = 0; it < (1 << 24); ++it) {
-            unsigned int c;
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(c) : "l"(counter) : "memory");
-            if (c >= nblocks) { ok = 1; break; }
+        int ok = 1;
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            atomicExch(bar, 0u);
+            __threadfence();
+            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+        } else {
+            ok = 0;
+            for (int it = 0; it < (1 << 24); ++it) {
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
+                if (cur != gen) { ok = 1; break; }
+            }
         }
         ok_s = ok;
     }
@@ -267,6 +276,19 @@ __device__ __forceinline__ float reduce_slice(const float *__restrict__ partials
     }
     return s;
 }
+// loss_out[0..2] += sum over the CTAs' loss partials (lane l adds blocks l, l + 32, ... in ascending order, then a fixed
+// shuffle tree: bit-reproducible), loss_out[3] += rows.  One full warp.
+__device__ __forceinline__ void add_loss_sums(const double *loss_partials, int nblocks, double *loss_out, double rows, int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int bl = lane; bl < nblocks; bl += 32) {
+        a0 += __ldcg(loss_partials + bl * 4); a1 += __ldcg(loss_partials + bl * 4 + 1); a2 += __ldcg(loss_partials + bl * 4 + 2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) { loss_out[0] += a0; loss_out[1] += a1; loss_out[2] += a2; loss_out[3] += rows; }
+}
 __device__ __forceinline__ float reduce_tree(float (&t)[RED_SL]) {
 #pragma unroll
     for (int w = RED_SL / 2; w > 0; w >>= 1)
@@ -278,6 +300,15 @@ __device__ __forceinline__ float reduce_tree(float (&t)[RED_SL]) {
 // optional phase timestamps of CTA 0 (PRL_TC_TIMING=1 in the environment prints them after the launch; debugging aid)
 __device__ long long g_tc_clock[32];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_clock[i] = clock64(); } while (0)
+// per-CTA wall-clock marks (ns): [cta][0] first instruction, [1] tiles done, [2] partials written, [3] last instruction
+__device__ unsigned long long g_tc_span[160 * 4 + 8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+#define TC_SPAN0(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_span[640 + (i)] = globaltimer_ns(); } while (0)
+#define TC_SPAN(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_tc_span[blockIdx.x * 4 + (i)] = globaltimer_ns(); } while (0)
 
 // ===================================================================================================== the kernel
 // NA = compile-time bound of the output widths (action_dim rounded up to 2, 4 or 8): the per-output loops unroll over it
@@ -299,6 +330,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const int r = rq * 32 + lane, j0 = TC_W * q;    // row of the tile, first feature of this thread
     const int O = L.O, A = L.A;
     TC_STAMP(0);
+    TC_SPAN(0);
 
     // ---- carve shared memory (all pointers derive from smem_raw so they stay in the shared state space)
     unsigned char *sW = smem_raw, *sF = sW + 3 * PIECE, *sDZ = sF + 3 * PIECE, *sX = sDZ + 4 * PIECE;
@@ -640,6 +672,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 
         // ================= read the accumulators out: tensor memory -> this block's partial-gradient row
         TC_STAMP(13);
+        TC_SPAN(1);
         if (it > 0) mma_ok &= mbar_wait(&bars[3], (it - 1) & 1);
         fence_after_sync();
         TC_STAMP(14);
@@ -713,11 +746,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     __syncthreads();
     if (is_mma_warp) tmem_dealloc(D.tmem, TM_COLS);
     TC_STAMP(16);
+    TC_SPAN(2);
+    TC_SPAN(3);
     if (!opt.params_rw) return;
 
     // ================= fused optimiser tail: reduce -> clip_grad_norm_ -> AdamW on this CTA's slice of the parameters
     const int nb = gridDim.x;
     if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    TC_SPAN0(0);
     const int S = (P + nb - 1) / nb, i0 = blockIdx.x * S, n_i = max(0, min(S, P - i0));   // 61 for P = 9 027 on 148 CTAs
     constexpr int RC = 64;                                            // parameters reduced per pass
     float *sl_part = reinterpret_cast<float *>(smem_raw);             // [RED_SL][RC] slice sums
@@ -726,6 +762,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const bool sharded = opt.world > 1;
     // destination of the locally reduced gradient: the final gradient buffer, or (sharded) my peer-visible exchange buffer
     float *gdst = sharded ? opt.peers[opt.rank] + (int)(opt_step & 1) * opt.gstride : opt.grad;
+    // losses of the whole launch (one warp of CTA 0; the other CTAs' loss partials were written before the first grid barrier)
+    if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
     for (int c0 = 0; c0 < n_i; c0 += RC) {
         const int nc = min(RC, n_i - c0);
         for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
@@ -745,17 +783,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         if (tid == 0)
             for (int k = 0; k < nc; ++k) ssum += sq[k];
     }
-    if (tid == 0 && blockIdx.x == 0) {   // losses of the whole launch (same bookkeeping as k_reduce_partials_tc); the other
-        // CTAs' loss partials are visible: they were written before the first grid barrier
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int bl = 0; bl < nb; ++bl) { a0 += loss_partials[bl * 4]; a1 += loss_partials[bl * 4 + 1]; a2 += loss_partials[bl * 4 + 2]; }
-        if (opt.loss_out) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
-    }
     if (sharded) {
         // ---- gradient exchange over peer memory: my reduced slice sits in my exchange buffer; once every CTA has written
         // its slice, CTA 0 raises my flag on every rank; then each CTA sums the W ranks' buffers over its slice in rank
         // order (identical result on every rank) - the allreduce, without leaving the kernel
-        if (!grid_barrier(opt.sync + 2, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+        if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
         const unsigned int epoch = (unsigned int)opt_step;
         const int flag_off = 2 * opt.gstride;   // in 4-byte words
         if (blockIdx.x == 0 && tid < opt.world) {
@@ -792,7 +824,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         }
     }
     if (tid == 0) opt.sumsq[blockIdx.x] = ssum;
-    if (!grid_barrier(opt.sync + 1, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    TC_SPAN0(1);
+    if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    TC_SPAN0(2);
     __shared__ float coef_s;
     if (warp == 0) {
         // total squared norm in a fixed order: lane l adds partials l, l + 32, ...; then a fixed shuffle tree
@@ -811,6 +845,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         }
     }
     __syncthreads();
+    TC_SPAN0(3);
     {
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
         const float step_size = (float)((double)opt.lr / (1.0 - opt_p1)), bc2_sqrt = (float)sqrt(1.0 - opt_p2);
@@ -826,6 +861,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             opt.params_rw[i] = pv; opt.m[i] = mi; opt.v[i] = vi;
         }
     }
+    TC_SPAN(3);
 }
 
 // grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x 16 block slices per
@@ -846,12 +882,7 @@ k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int
         for (int u = 0; u < RED_SL; ++u) t[u] = part[u][p];
         grad[i] = reduce_tree(t);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 3 && loss_out) {
-        double t = 0.0;
-        for (int bl = 0; bl < nblocks; ++bl) t += loss_partials[bl * 4 + threadIdx.x];
-        loss_out[threadIdx.x] += t;
-        if (threadIdx.x == 0) loss_out[3] += rows;
-    }
+    if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) add_loss_sums(loss_partials, nblocks, loss_out, rows, threadIdx.x);
 }
 
 static int tc_grid(int64_t b) {
@@ -905,7 +936,6 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
         opt = *optp;
         opt.sync = reinterpret_cast<unsigned int *>(ws) + 1;
         opt.sumsq = loss_partials + (size_t)grid * 4;
-        PRL_CUDA(cudaMemsetAsync(opt.sync, 0, 3 * sizeof(unsigned int), st));
     }
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -930,6 +960,19 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
                         "readout %lld, tail %lld | kernel %lld\n", who,
                 c[1] - c[0], c[2] - c[1], c[4] - c[2], c[5] - c[4], c[6] - c[5], c[8] - c[6], c[9] - c[8], c[11] - c[9], c[12] - c[11], c[13] - c[1],
                 c[14] - c[13], c[15] - c[14], c[16] - c[15], c[16] - c[0]);
+        static unsigned long long sp[160 * 4 + 8];
+        PRL_CUDA(cudaMemcpyFromSymbol(sp, g_tc_span, sizeof sp));
+        unsigned long long t0 = ~0ull, s_max = 0, e1_min = ~0ull, e1_max = 0, e2_max = 0, e3_max = 0;
+        for (int c2 = 0; c2 < grid && c2 < 160; ++c2) {
+            t0 = sp[c2 * 4] < t0 ? sp[c2 * 4] : t0; s_max = sp[c2 * 4] > s_max ? sp[c2 * 4] : s_max;
+            e1_min = sp[c2 * 4 + 1] < e1_min ? sp[c2 * 4 + 1] : e1_min; e1_max = sp[c2 * 4 + 1] > e1_max ? sp[c2 * 4 + 1] : e1_max;
+            e2_max = sp[c2 * 4 + 2] > e2_max ? sp[c2 * 4 + 2] : e2_max; e3_max = sp[c2 * 4 + 3] > e3_max ? sp[c2 * 4 + 3] : e3_max;
+        }
+        fprintf(stderr, "[%s] grid %d wall clock (ns from the first CTA start): last CTA start %llu | tiles done: first %llu, last %llu | partials written %llu | "
+                        "kernel end %llu | CTA0: start %llu tiles %llu end %llu\n", who, grid, s_max - t0, e1_min - t0, e1_max - t0, e2_max - t0, e3_max - t0,
+                sp[0] - t0, sp[1] - t0, sp[3] - t0);
+        if (optp) fprintf(stderr, "[%s] CTA0 tail: barrier 1 passed %llu, slice reduced %llu, barrier 2 passed %llu, norm known %llu, end %llu\n", who, sp[640] - t0,
+                          sp[641] - t0, sp[642] - t0, sp[643] - t0, sp[3] - t0);
     }
     if (!optp) k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
     return check_launch(who);
@@ -1008,6 +1051,9 @@ int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream) {
     PRL_REQUIRE(ws && status_host, "prl_ppo_grad_tc_status: bad arguments");
     PRL_CUDA(cudaMemcpyAsync(status_host, ws, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    // a timed-out grid barrier leaves its arrival count behind: clear it so that the workspace can be used again
+    if (*status_host == 2 || *status_host == 3)
+        PRL_CUDA(cudaMemsetAsync(const_cast<float *>(ws) + 1, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
     return PRL_OK;
 }
 

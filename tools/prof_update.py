@@ -17,7 +17,24 @@ a = t.from_numpy(rng.integers(0, A, (N, 1)).astype(np.float32)).cuda()
 logp, _, _ = ops.policy_evaluate(params, False, O, A, s, a)
 adv = t.randn(N, device="cuda"); ret = t.randn(N, device="cuda")
 grad = t.zeros_like(params); loss = t.zeros(4, dtype=t.float64, device="cuda")
-if path == "tc":
+if path == "step":   # fused gradient + clip + AdamW (cooperative launch), eager and as a replayed CUDA graph
+    from prl_b200.optim import FusedAdamW
+    opt = FusedAdamW(params, 1e-4)
+    ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
+    fn = lambda: ops.ppo_step_tc(params, False, O, A, s, a, logp, adv, ret, 0.2, 1.0 / N, grad, loss, opt, ws)
+    if os.environ.get("PRL_PROF_GRAPH"):
+        side = t.cuda.Stream(); side.wait_stream(t.cuda.current_stream())
+        gr = t.cuda.CUDAGraph()
+        with t.cuda.stream(side):
+            gr.capture_begin()
+            for _ in range(32):
+                fn()
+            gr.capture_end()
+        t.cuda.current_stream().wait_stream(side)
+        one = fn
+        fn = gr.replay
+        N = N * 32
+elif path == "tc":
     ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
     fn = lambda: ops.ppo_grad_tc(params, False, O, A, s, a, logp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
 else:
