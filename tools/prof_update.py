@@ -50,3 +50,18 @@ for _ in range(reps):
 e1.record(); t.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 print(f"{path} N={N}: {ms * 1e3:.1f} us per call, {N / ms / 1e3:.1f} M rows/s, {N * 51840 / ms / 1e9:.2f} TFLOP/s algorithmic")
+if os.environ.get("PRL_PROF_EVAL"):
+    NE = 8_388_608
+    se = t.from_numpy(rng.uniform(-1, 1, (NE, O)).astype(np.float32)).cuda()
+    ae = t.from_numpy(rng.integers(0, A, (NE, 1)).astype(np.float32)).cuda()
+    lo, vo = t.empty(NE, device="cuda"), t.empty(NE, device="cuda")
+    ent = t.zeros(1, dtype=t.float64, device="cuda")
+    for _ in range(2):
+        ops.policy_evaluate(params, False, O, A, se, ae, entropy_sum=ent, logp=lo, value=vo)
+    t.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        ops.policy_evaluate(params, False, O, A, se, ae, entropy_sum=ent, logp=lo, value=vo)
+    e1.record(); t.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"evaluate N={NE}: {ms:.3f} ms, {NE / ms / 1e3:.1f} M rows/s, {NE * 17280 / ms / 1e9:.2f} TFLOP/s fp32")
