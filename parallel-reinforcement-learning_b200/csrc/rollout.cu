@@ -4,6 +4,7 @@
 // Reference: /root/reference/AsyncTools/AsyncPPO.py:11-146, AsyncTools/utils.py:1-50, PPO/PPO.py:82-96.
 #include "envs.cuh"
 #include "policy.cuh"
+#include "tiled_mlp.cuh"
 
 namespace prl {
 
@@ -268,24 +269,30 @@ __global__ void k_zero_i32(int32_t *p, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ PPO.get_action
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(EV_THREADS, 2)
 k_policy_act(const float *__restrict__ params, PolicyLayout L, float action_scaling, const float *__restrict__ states,
              const int32_t *__restrict__ row_ids, int64_t n, uint64_t seed, uint64_t call_index, void *__restrict__ actions,
              float *__restrict__ dist) {
     extern __shared__ __align__(16) float smem[];
-    const ActSmem W = stage_act_weights(smem, params, L);
+    const EvSmem S = ev_layout(L, L.n_heads - 1);   // policy heads only (get_action does not touch the critic)
+    ev_stage_weights(smem, S, params, L);
+    const int tid = threadIdx.x, O = L.O;
+    const int64_t row0 = (int64_t)blockIdx.x * EV_ROWS;
+    const int rows = (int)min((int64_t)EV_ROWS, n - row0);
+    float *sX = smem + S.x;
+    for (int i = tid; i < EV_ROWS * O; i += EV_THREADS) sX[i] = i < rows * O ? __ldg(states + row0 * O + i) : 0.f;
     __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (row >= n) return;
-    float *col = W.scratch + threadIdx.x;
-    const float *x = states + row * L.O;
-    policy_forward(W, L.O, [&](int i) { return __ldg(x + i); }, col, TPB);
+    ev_forward_tile(smem, S, L);
+    __syncthreads();
+    if (tid >= rows) return;
+    const int64_t row = row0 + tid;
+    float *o = smem + S.out + tid * S.so;
     Philox ph(seed);
     const uint32_t rid = row_ids ? (uint32_t)row_ids[row] : (uint32_t)row;
     uint32_t r[4];
     if (!L.cont) {
         ph(rid, (uint32_t)call_index, action_stream_word(0), (uint32_t)(call_index >> 32), r);
-        const int a = sample_categorical(col, TPB, L.A, u01f(r[0]), dist ? dist + row * L.A : nullptr);
+        const int a = ev_sample_categorical(o, L.A, u01f(r[0]), dist ? dist + row * L.A : nullptr);
         static_cast<int64_t *>(actions)[row] = a;
     } else {
         float *out = static_cast<float *>(actions) + row * L.A;
@@ -295,8 +302,8 @@ k_policy_act(const float *__restrict__ params, PolicyLayout L, float action_scal
                 ph(rid, (uint32_t)call_index, action_stream_word(a >> 2), (uint32_t)(call_index >> 32), r);
                 normals4(r, nrm);
             }
-            const float mu = col[(HID + a) * TPB];
-            const float ls = col[(HID + L.A + a) * TPB];
+            const float mu = o[S.col[0] + a];
+            const float ls = o[S.col[1] + a];
             const float sd = softplus_t(fminf(fmaxf(ls, -2.f), 2.f));
             const float tril = sqrtf(sd * sd);  // cholesky of diag(std^2)
             out[a] = tanhf(fmaf(tril, nrm[a & 3], mu)) * action_scaling;
@@ -306,20 +313,24 @@ k_policy_act(const float *__restrict__ params, PolicyLayout L, float action_scal
 }
 
 // ------------------------------------------------------------------------------------------------ fused worker()
+// One thread per env for the physics, sampling and bookkeeping; the policy forward of the CTA's 256 envs runs as one
+// register-tiled pass per step (tiled_mlp.cuh) between two barriers.  TAPED: actions come from a tape (teacher forcing,
+// parity tests and the env-step bandwidth benchmark), no network, 128 threads.
 template <class ENV, bool TAPED>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(EV_THREADS, 2)
 k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, float action_scaling, uint64_t seed,
           uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
           uint8_t *__restrict__ terminal, float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
           float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores) {
     extern __shared__ __align__(16) float smem[];
-    ActSmem W{};
+    constexpr int NT = TAPED ? TPB : EV_THREADS;
+    EvSmem S{};
     if constexpr (!TAPED) {
-        W = stage_act_weights(smem, params, L);
-        __syncthreads();
+        S = ev_layout(L, L.n_heads - 1);
+        ev_stage_weights(smem, S, params, L);   // made visible by the first barrier of the step loop
     }
     __shared__ double red[32];
-    const int e = blockIdx.x * TPB + threadIdx.x;
+    const int e = blockIdx.x * NT + threadIdx.x;
     const bool valid = e < E;
     bool alive = valid;
     double s[ENV::S];
@@ -327,12 +338,21 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
     double rsum = 0.0;
     int len = 0;
     Philox ph(seed);
-    float *col = TAPED ? nullptr : W.scratch + threadIdx.x;
     for (int t = 0; t < T_cap; ++t) {
-        if (!__any_sync(0xffffffffu, alive)) break;
+        float o[ENV::O];
+        if (alive) ENV::obs(s, o);
+        if constexpr (TAPED) {
+            if (!__any_sync(0xffffffffu, alive)) break;
+        } else {
+            // the whole CTA runs the forward while any of its envs is alive (finished envs feed zeros, results unused)
+            float *sX = smem + S.x + threadIdx.x * ENV::O;
+#pragma unroll
+            for (int c = 0; c < ENV::O; ++c) sX[c] = alive ? o[c] : 0.f;
+            if (!__syncthreads_or(alive)) break;
+            ev_forward_tile(smem, S, L);
+            __syncthreads();
+        }
         if (alive) {
-            float o[ENV::O];
-            ENV::obs(s, o);
             typename ENV::Action a;
             float a_store;
             if constexpr (TAPED) {
@@ -340,19 +360,19 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
                 else a = static_cast<const int32_t *>(tape)[(size_t)t * E + e];
                 a_store = (float)a;
             } else {
-                policy_forward(W, ENV::O, [&](int i) { return o[i]; }, col, TPB);
+                float *out = smem + S.out + threadIdx.x * S.so;
                 uint32_t r[4];
                 ph((uint32_t)e, (uint32_t)t, action_stream_word(0), (uint32_t)episode, r);
                 if constexpr (ENV::CONT) {
                     float nrm[4];
                     normals4(r, nrm);
-                    const float mu = col[HID * TPB];
-                    const float ls = col[(HID + ENV::A) * TPB];
+                    const float mu = out[S.col[0]];
+                    const float ls = out[S.col[1]];
                     const float sd = softplus_t(fminf(fmaxf(ls, -2.f), 2.f));
                     a = tanhf(fmaf(sqrtf(sd * sd), nrm[0], mu)) * action_scaling;
                     a_store = a;
                 } else {
-                    a = sample_categorical(col, TPB, ENV::A, u01f(r[0]), nullptr);
+                    a = ev_sample_categorical(out, ENV::A, u01f(r[0]), nullptr);
                     a_store = (float)a;
                 }
             }
@@ -512,10 +532,10 @@ int prl_policy_act(const float *params, int is_continuous, int obs_dim, int acti
     if (n == 0) return PRL_OK;
     PRL_REQUIRE(states && actions, "prl_policy_act: null pointer");
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    const size_t smem = act_smem_floats(L, TPB) * sizeof(float);
+    const size_t smem = (size_t)ev_layout(L, L.n_heads - 1).total * sizeof(float);
     PRL_REQUIRE(smem <= 227 * 1024, "prl_policy_act: observ_dim=%d action_dim=%d needs %zu B shared memory (> 227 KB)", obs_dim, action_dim, smem);
     PRL_CUDA(cudaFuncSetAttribute(k_policy_act, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_policy_act<<<cdiv(n, TPB), TPB, smem, (cudaStream_t)stream>>>(params, L, action_scaling, states, row_ids, n, seed, call_index, actions, dist);
+    k_policy_act<<<cdiv(n, EV_ROWS), EV_THREADS, smem, (cudaStream_t)stream>>>(params, L, action_scaling, states, row_ids, n, seed, call_index, actions, dist);
     return check_launch("k_policy_act");
 }
 
@@ -533,9 +553,9 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
             k_rollout<ENV, true><<<cdiv(E, TPB), TPB, 0, st>>>(E, T_cap, params, L, action_scaling, seed, episode, tape, state, elapsed,
                                                               terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores);
         } else {
-            const size_t smem = act_smem_floats(L, TPB) * sizeof(float);
+            const size_t smem = (size_t)ev_layout(L, L.n_heads - 1).total * sizeof(float);
             PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_rollout<ENV, false><<<cdiv(E, TPB), TPB, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
+            k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
                                                                  elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
                                                                  lengths, scores);
         }
