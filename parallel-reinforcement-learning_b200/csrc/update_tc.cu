@@ -155,17 +155,20 @@ struct TcDesc {          // base descriptors, K-major and MN-major views, built 
 };
 __device__ __forceinline__ uint64_t dadd(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-__device__ __forceinline__ void issue_forward(const TcDesc &D) {
-    constexpr uint32_t id = idesc_bf16(128, 128, 0, 0);
+// forward of head h: Z_h = F . W1_h^T  (W1 rows 64 h .. 64 h + 63 of the stacked [128][64] weight tile, N = 64), committed per
+// head so that the actor's epilogue starts while the critic's MMAs still run
+__device__ __forceinline__ void issue_forward(const TcDesc &D, int h) {
+    constexpr uint32_t id = idesc_bf16(128, 64, 0, 0);
     constexpr int TA[6] = {0, 0, 1, 1, 0, 2}, TB[6] = {0, 1, 0, 1, 2, 0};
+    const uint64_t wh = dadd(D.W_k, h * 64 * 16);
 #pragma unroll
     for (int t = 0; t < 6; ++t)
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-            mma_bf16_ss(D.tmem + TM_Z, dadd(D.F_k, TA[t] * PIECE + s * 2 * CHUNK), dadd(D.W_k, TB[t] * PIECE + s * 2 * CHUNK), id, (t | s) != 0);
+            mma_bf16_ss(D.tmem + TM_Z + 64 * h, dadd(D.F_k, TA[t] * PIECE + s * 2 * CHUNK), dadd(wh, TB[t] * PIECE + s * 2 * CHUNK), id, (t | s) != 0);
 }
-__device__ __forceinline__ void issue_head_backward(const TcDesc &D, int h, bool first_tile) {
-    constexpr uint32_t id_d = idesc_bf16(128, 64, 0, 1), id_w = idesc_bf16(128, 64, 1, 1);
+__device__ __forceinline__ void issue_head_dgrad(const TcDesc &D, int h) {
+    constexpr uint32_t id_d = idesc_bf16(128, 64, 0, 1);
     constexpr int TA[6] = {0, 0, 1, 1, 0, 2}, TB[6] = {0, 1, 0, 1, 2, 0};
     // dgrad: DF (+)= DZ_h . W1_h   (B: MN-major view of W1, head h starts 64 rows = 1024 B in; 16 j's per step = 256 B)
     const uint64_t wh = dadd(D.W_mn, h * 64 * 16);
@@ -174,6 +177,9 @@ __device__ __forceinline__ void issue_head_backward(const TcDesc &D, int h, bool
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             mma_bf16_ss(D.tmem + TM_DF, dadd(D.DZ_k, TA[t] * PIECE + s * 2 * CHUNK), dadd(wh, TB[t] * PIECE + s * 256), id_d, (h | t | s) != 0);
+}
+__device__ __forceinline__ void issue_head_wgrad(const TcDesc &D, int h, bool first_tile) {
+    constexpr uint32_t id_w = idesc_bf16(128, 64, 1, 1);
     // wgrad: DW_h[(piece window, j)][k] += sum_r DZ[r][.] F[r][k]; windows [p0|p1] x f0, f1, f2 and [p2|0] x f0
     const uint32_t dw = D.tmem + TM_DW + 64 * h;
 #pragma unroll
@@ -319,7 +325,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
               float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
               int *__restrict__ status, TcOptimizer opt) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t bars[4];          // MMA completion: forward, actor backward, critic backward, trunk wgrad
+    __shared__ uint64_t bars[6];          // MMA completion: actor forward, actor backward, critic dgrad, trunk wgrad, critic wgrad, critic forward
     __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
     __shared__ uint32_t tmem_slot;
     __shared__ double red[32];
@@ -367,7 +373,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&bars[i], 1); mbar_init(&sbar[i], TC_COMPUTE); }
+        for (int i = 0; i < 4; ++i) mbar_init(&sbar[i], TC_COMPUTE);
+        for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
     if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);
@@ -409,15 +416,16 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             const uint32_t parity = it & 1;
             mma_ok &= mbar_wait(&sbar[0], parity);
             fence_after_sync();
-            if (elect_one()) { issue_forward(D); mma_commit(&bars[0]); }
+            if (elect_one()) { issue_forward(D, 0); mma_commit(&bars[0]); issue_forward(D, 1); mma_commit(&bars[5]); }
             __syncwarp();
             mma_ok &= mbar_wait(&sbar[1], parity);
             fence_after_sync();
-            if (elect_one()) { issue_head_backward(D, 0, it == 0); mma_commit(&bars[1]); }
+            if (elect_one()) { issue_head_dgrad(D, 0); issue_head_wgrad(D, 0, it == 0); mma_commit(&bars[1]); }
             __syncwarp();
             mma_ok &= mbar_wait(&sbar[2], parity);
             fence_after_sync();
-            if (elect_one()) { issue_head_backward(D, 1, it == 0); mma_commit(&bars[2]); }
+            // the trunk backward needs DF (both dgrads) only: the critic's wgrad gets its own completion barrier
+            if (elect_one()) { issue_head_dgrad(D, 1); mma_commit(&bars[2]); issue_head_wgrad(D, 1, it == 0); mma_commit(&bars[4]); }
             __syncwarp();
             mma_ok &= mbar_wait(&sbar[3], parity);
             fence_after_sync();
@@ -532,6 +540,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 load16(sh + j0, gw);
                 load16(sh + HID + j0, gb);
                 float zhat[TC_W], rstd[2], sg[TC_W];
+                if (h == 1) { mma_ok &= mbar_wait(&bars[5], parity); fence_after_sync(); }   // critic forward complete
                 tmem_ld16w(lane_base + TM_Z + 64 * h + j0, zhat);
                 gn_normalize16(zhat, rstd);
                 float po[NA];
@@ -646,7 +655,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 trunk_pre(zh0, rs0);   // recomputed (cheap) rather than kept in registers across the head phases
                 load16(s_g0w + j0, g0w);
                 load16(s_g0b + j0, g0b);
-                mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final; DZ free again
+                mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final
                 fence_after_sync();
                 if (it == 0) TC_STAMP(11);
                 tmem_ld16w(lane_base + TM_DF + j0, df);
@@ -664,6 +673,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     colsum16(df, acc + HID);
                 }
                 gn_backward16(df, zh0, rs0, g0w);
+                mma_ok &= mbar_wait(&bars[4], parity);    // critic wgrad complete -> DZ free again
                 store_pieces16(sDZ, r, q, df);
                 staged(&sbar[3]);
                 if (it == 0) TC_STAMP(12);
