@@ -348,29 +348,50 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     float *s_po = s_head1 + 2 * HID + L.head[1].out * HID + round4(L.head[1].out);   // [4 q][128 r][NA] partial head outputs
     float *s_red = s_po + 4 * TC_ROWS * NA;                                            // [4 rq][NQ][64] final combine
 
-    // ---- stage parameters: fp32 small ones; W1 of both heads as bf16x3 in the operand layout (row n = h*64 + j)
-    stage_transposed(s_w0t, params + L.w0, HID, O);
-    stage_copy(s_g0w, params + L.g0w, HID);
-    stage_copy(s_g0b, params + L.g0b, HID);
-    for (int h = 0; h < 2; ++h) {
-        float *sh = h ? s_head1 : s_head0;
-        stage_copy(sh, params + L.head[h].gw, HID);
-        stage_copy(sh + HID, params + L.head[h].gb, HID);
-        stage_copy(sh + 2 * HID, params + L.head[h].w2, L.head[h].out * HID);
-        stage_copy(sh + 2 * HID + L.head[h].out * HID, params + L.head[h].b2, L.head[h].out);
-    }
-    if (!is_mma_warp) {
-        // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
-        const float *wrow = params + L.head[r >> 6].w1 + (r & 63) * HID + j0;
+    // ---- stage parameters: fp32 small ones; W1 of both heads as bf16x3 in the operand layout (row n = h*64 + j).
+    // Every global load is issued before the first dependent shared-memory store (one exposed memory latency, not ten).
+    {
         float v[TC_W];
+        const int n_small0 = HID * O, n_small1 = n_small0 + 2 * HID, n_h0 = 2 * HID + L.head[0].out * HID + L.head[0].out,
+                  n_h1 = 2 * HID + L.head[1].out * HID + L.head[1].out, n_small = n_small1 + n_h0 + n_h1;
+        if (!is_mma_warp) {
+            // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
+            const float4 *wrow = reinterpret_cast<const float4 *>(params + L.head[r >> 6].w1 + (r & 63) * HID + j0);
+            if ((L.head[r >> 6].w1 & 3) == 0) {   // warp-uniform (a warp's rows belong to one head)
 #pragma unroll
-        for (int k = 0; k < TC_W; ++k) v[k] = __ldg(wrow + k);
-        store_pieces16(sW, r, q, v);
-        // zero slot behind the three DZ pieces; X pieces (columns >= O stay zero for the whole kernel)
+                for (int k = 0; k < 4; ++k) { const float4 t = __ldg(wrow + k); v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+            } else {
+                const float *ws = reinterpret_cast<const float *>(wrow);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) *reinterpret_cast<uint4 *>(sDZ + 3 * PIECE + (2 * q + c) * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
-        if (q == 0)
-            for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+                for (int k = 0; k < TC_W; ++k) v[k] = __ldg(ws + k);
+            }
+        }
+        // small parameters: w0 (stored transposed), then three blocks that are contiguous both in `params` and in shared
+        // memory: {g0w, g0b}, head 0 {gw, gb, w2, b2}, head 1 {gw, gb, w2, b2}
+        for (int base = 0; base < n_small; base += 2 * TC_THREADS) {
+            float sv[2];
+            float *dst[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = base + u * TC_THREADS + tid;
+                dst[u] = nullptr;
+                if (i < n_small0) { const int j = i / O, o = i - j * O; dst[u] = s_w0t + o * HID + j; sv[u] = __ldg(params + L.w0 + i); }
+                else if (i < n_small1) { dst[u] = s_g0w + (i - n_small0); sv[u] = __ldg(params + L.g0w + (i - n_small0)); }
+                else if (i < n_small1 + n_h0) { dst[u] = s_head0 + (i - n_small1); sv[u] = __ldg(params + L.head[0].gw + (i - n_small1)); }
+                else if (i < n_small) { dst[u] = s_head1 + (i - n_small1 - n_h0); sv[u] = __ldg(params + L.head[1].gw + (i - n_small1 - n_h0)); }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (dst[u]) *dst[u] = sv[u];
+        }
+        if (!is_mma_warp) {
+            store_pieces16(sW, r, q, v);
+            // zero slot behind the three DZ pieces; X pieces (columns >= O stay zero for the whole kernel)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) *reinterpret_cast<uint4 *>(sDZ + 3 * PIECE + (2 * q + c) * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+            if (q == 0)
+                for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+        }
     }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&sbar[i], TC_COMPUTE);
