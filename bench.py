@@ -318,71 +318,100 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cs, csec = cpu_port_steps(args.cpu_sample_envs, T, args.k_epochs, args.mini_batch, 1, 0, threads)
+        n_cpu = 4 * args.cpu_sample_envs   # one untrained-policy step: ~20 env-steps per env, ~10 s of host work
+        cs, csec = cpu_port_steps(n_cpu, T, args.k_epochs, args.mini_batch, 1, 0, threads)
         out["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"1 step of {args.cpu_sample_envs} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
+                               "sample": f"1 step of {n_cpu} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
                                          f"{cs} env-steps in {csec:.1f} s"}
     print(json.dumps(out), flush=True)
 
 
 def hbm_microbench(pk, E=65536, T=128):
     """The HBM-bound kernels of the path in isolation (outside the timed region): achieved GB/s at SURVEY 8(d)'s
-    algorithmic bytes per unit, CUDA events on the launching stream, inputs larger than L2 or L2 flushed between calls."""
-    import numpy as np
+    algorithmic bytes per unit at the C2 shapes (E = 65 536, T = 128).  Each figure is the average over ROT launches that
+    run back to back on ROT DIFFERENT buffer sets (together several times the 126 MB L2, so every launch streams from
+    HBM and launch latency is amortised as it is inside a step), CUDA events on the launching stream."""
     import torch as t
 
     from prl_b200 import ops
 
     dev = t.device("cuda", t.cuda.current_device())
-    flush = t.empty(256 << 20, dtype=t.uint8, device=dev)
+    ROT = 4
 
-    def timeit(fn, reps=8):
-        fn()
+    def timeit(fns, reps=5):
+        for f in fns:
+            f()
+        t.cuda.synchronize()
         ms = 0.0
         for _ in range(reps):
-            flush.fill_(0)
             e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
+            e0.record()
+            for f in fns:
+                f()
+            e1.record()
             t.cuda.synchronize()
             ms += e0.elapsed_time(e1)
-        return ms / reps
+        return ms / reps / len(fns)
 
     out = {}
     N = E * T
-    r = t.ones(N, device=dev); v = t.rand(N, device=dev); ret = t.empty(N, device=dev); adv = t.empty(N, device=dev)
-    for name, ep in (("gae_flat_T128", T), ("gae_flat_T20", 20)):
-        d = t.zeros(N, device=dev); d[ep - 1::ep] = 1.0
-        ms = timeit(lambda: ops.gae(r, d, v, 0.995, 0.95, out=ret))
-        out[name] = {"GB/s": N * 16 / ms / 1e6, "ms": ms, "bytes_per_transition": 16}
-    r2, d2, v2 = r.view(T, E), t.zeros(T, E, device=dev), v.view(T, E)
-    d2[T - 1] = 1.0
+    sets = []
+    for _ in range(ROT):
+        sets.append(dict(r=t.ones(N, device=dev), v=t.rand(N, device=dev), ret=t.empty(N, device=dev), adv=t.empty(N, device=dev),
+                         d=t.zeros(N, device=dev), stats=t.zeros(4, dtype=t.float64, device=dev)))
+    ws = t.empty(64, dtype=t.uint8, device=dev)
     lens = t.full((E,), T, dtype=t.int32, device=dev)
-    ms = timeit(lambda: ops.gae_columns(r2, d2, v2, lens, 0.995, 0.95, out=ret.view(T, E)))
+    gen = t.Generator(device=dev); gen.manual_seed(7)
+    for name, ep in (("gae_flat_T128", T), ("gae_flat_T20", 20), ("gae_flat_ragged_20_128", None)):
+        for S in sets:
+            S["d"].zero_()
+            if ep is None:   # ragged episodes of 20..128 steps, as a partly trained CartPole policy produces
+                ends = t.cumsum(t.randint(20, T + 1, (2 * E,), device=dev, generator=gen), 0) - 1
+                S["d"][ends[ends < N]] = 1.0
+                S["d"][N - 1] = 1.0
+            else:
+                S["d"][ep - 1::ep] = 1.0
+        ms = timeit([lambda S=S: ops.gae(S["r"], S["d"], S["v"], 0.995, 0.95, out=S["ret"], ws=ws) for S in sets])
+        out[name] = {"GB/s": N * 16 / ms / 1e6, "ms": ms, "bytes_per_transition": 16}
+    for S in sets:
+        S["d"].zero_(); S["d"].view(T, E)[T - 1] = 1.0
+    ms = timeit([lambda S=S: ops.gae_columns(S["r"].view(T, E), S["d"].view(T, E), S["v"].view(T, E), lens, 0.995, 0.95, out=S["ret"].view(T, E))
+                 for S in sets])
     out["gae_columns_T128"] = {"GB/s": N * 16 / ms / 1e6, "ms": ms, "bytes_per_transition": 16}
-    stats = t.zeros(4, dtype=t.float64, device=dev)
-    ms = timeit(lambda: (stats.zero_(), ops.adv_normalize(ret, v, stats=stats, phase=3, out=adv)))
+    ms = timeit([lambda S=S: (S["stats"].zero_(), ops.adv_normalize(S["ret"], S["v"], stats=S["stats"], phase=3, out=S["adv"])) for S in sets])
     out["adv_normalize"] = {"GB/s": N * 20 / ms / 1e6, "ms": ms, "bytes_per_transition": 20}
-    # standalone env step (per-step API), all envs active, 2^20 envs: 102 B per env-step (CartPole)
-    E2 = 1 << 20
+    del sets
+    # device VecMemory -> PPO.memory (prl_buffer_transfer), every env with a full-length episode: 56 B per transition
+    bufs = [ops.RolloutBuffer(E, T, 4, 1) for _ in range(2)]
+    mems = [[t.empty(N, 4, device=dev), t.empty(N, 1, device=dev), t.empty(N, device=dev), t.empty(N, device=dev)] for _ in range(2)]
+    total = t.zeros(1, dtype=t.int64, device=dev)
+
+    def xfer(b, m):
+        b.lengths.fill_(T)
+        b.transfer(*m, 0, total)
+    ms = timeit([lambda b=b, m=m: xfer(b, m) for b, m in zip(bufs, mems)])
+    out["buffer_transfer"] = {"GB/s": N * 56 / ms / 1e6, "ms": ms, "bytes_per_transition": 56}
+    del mems
+    # standalone env step (per-step API), all envs active, 2^22 envs (428 MB per launch > L2): 102 B per env-step (CartPole)
+    E2 = 1 << 22
     sim = ops.EnvState("CartPole-v1", E2, 1 << 30)
     sim.reset(1, 1)
     idx = t.arange(E2, dtype=t.int32, device=dev)
     acts = t.randint(0, 2, (E2,), dtype=t.int32, device=dev)
-    ms = timeit(lambda: sim.step(idx, E2, acts))
+    ms = timeit([lambda: sim.step(idx, E2, acts)] * 3)
     out["env_step_cartpole"] = {"GB/s": E2 * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "envs": E2}
+    del sim, idx, acts
     # teacher-forced fused rollout (physics + TimeLimit + mask + buffer write, no policy): E x T env-steps
-    sim = ops.EnvState("CartPole-v1", E, T)
-    buf = ops.RolloutBuffer(E, T, 4, 1)
+    sims = [ops.EnvState("CartPole-v1", E, T) for _ in range(2)]
     tape = t.randint(0, 2, (T, E), dtype=t.int32, device=dev)
     scores = t.zeros(2, dtype=t.float64, device=dev)
-    steps = [0.0]
 
-    def taped():
+    def taped(sim, buf):
         sim.reset(1, 1)
-        scores.zero_()
         ops.rollout(sim, buf, None, 1.0, 0, 1, scores, tape=tape)
-    ms = timeit(taped)
+    taped(sims[0], bufs[0]); scores.zero_(); taped(sims[0], bufs[0])
     n_steps = float(scores.cpu()[1])
+    ms = timeit([lambda s_=s_, b=b: taped(s_, b) for s_, b in zip(sims, bufs)])
     out["rollout_taped_cartpole"] = {"GB/s": n_steps * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "env_steps": n_steps}
     for k in out:
         out[k]["frac_of_" + pk["source"] + "_hbm"] = out[k]["GB/s"] / pk["hbm"]

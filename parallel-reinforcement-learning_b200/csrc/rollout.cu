@@ -263,6 +263,87 @@ __global__ void k_transfer(int E, int T_cap, int C, const float *__restrict__ sr
     }
 }
 
+// All fields in one launch.  The channels of the four fields (observation components, action components, reward, done)
+// are packed into groups of <= 4; a warp moves one 32(t) x 32(e) tile of one group at a time: float4 loads (4 time rows x
+// 128 bytes per warp instruction, 8 in flight per lane) fill [channel][t][e] shared-memory tiles, the warp then turns
+// around (lane = t) and writes env-major rows - a whole float4 row per lane when the group is channels
+// 4k..4k+3 of a field whose width is a multiple of 4 (CartPole observations), so the writes are 512 contiguous bytes.
+struct XferGroup {
+    const float *src[4];   // channel plane: element (t, e) at src[t * sstride + e]
+    float *dst[4];         // element (n) at dst[n * dC]
+    int64_t sstride[4];
+    int dC[4];
+    int n, vec;            // channels in the group; vec: one float4 store at dst[0] + n * 4 ... (dC == 4 k, 16-byte aligned)
+};
+constexpr int XF_MAX_GROUPS = 8;
+struct XferPlan {
+    int ngroups;
+    XferGroup g[XF_MAX_GROUPS];
+};
+constexpr int XF_WARPS = 4;
+__global__ void __launch_bounds__(XF_WARPS * 32)
+k_transfer_tiles(int E, int T_cap, XferPlan plan, const int32_t *__restrict__ len, const int64_t *__restrict__ offsets, int64_t capacity) {
+    extern __shared__ __align__(16) float xf_smem[];
+    __shared__ int64_t s_off[XF_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float(*tile)[32][33] = reinterpret_cast<float(*)[32][33]>(xf_smem + (size_t)w * 4 * 32 * 33);
+    const int e = blockIdx.x * 32 + lane;
+    const int t0 = (blockIdx.y * XF_WARPS + w) * 32;
+    const int my_len = e < E ? min(len[e], T_cap) : 0;
+    const int max_len = __reduce_max_sync(0xffffffffu, my_len);
+    if (t0 >= max_len) return;
+    const int64_t my_off = e < E ? offsets[e] : 0;
+    const int t = t0 + lane;   // this lane's time step in the write phase
+    // once per tile: destination row of (env ee, this lane's t) = s_off[ee] + lane; bit ee of `ok` = that row exists
+    s_off[w][lane] = my_off + t0;
+    unsigned ok = 0;
+#pragma unroll
+    for (int ee = 0; ee < 32; ++ee) {
+        const int l = __shfl_sync(0xffffffffu, my_len, ee);
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, ee);
+        ok |= (unsigned)(t < l && off + t < capacity) << ee;
+    }
+    for (int gi = 0; gi < plan.ngroups; ++gi) {
+        const int gn = plan.g[gi].n;
+        __syncwarp();          // the previous group's tile has been read
+        // float4 loads: lane l fetches envs 4 (l % 8) .. + 3 of time rows l / 8 + 4 j; the scalar stores into the 33-word rows
+        // are conflict-free (bank = row + column).  Rows past an env's length hold stale data that is never written out.
+        {
+            const int lrow = lane >> 3, lcol = (lane & 7) * 4;
+            const int rows = min(32, min(max_len, T_cap) - t0);
+            const bool col_in = blockIdx.x * 32 + lcol < E;
+            for (int cc = 0; cc < gn; ++cc) {
+                const int64_t ss = plan.g[gi].sstride[cc];
+                const float *sp = plan.g[gi].src[cc] + blockIdx.x * 32 + lcol + (int64_t)(t0 + lrow) * ss;
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (col_in && 4 * j + lrow < rows) v[j] = __ldcs(reinterpret_cast<const float4 *>(sp + (int64_t)(4 * j) * ss));
+                float *tp = &tile[cc][lrow][lcol];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (col_in && 4 * j + lrow < rows) { float *q = tp + 4 * j * 33; q[0] = v[j].x; q[1] = v[j].y; q[2] = v[j].z; q[3] = v[j].w; }
+            }
+        }
+        __syncwarp();
+        if (plan.g[gi].vec) {
+            float4 *d4 = reinterpret_cast<float4 *>(plan.g[gi].dst[0]) + (int64_t)lane * (plan.g[gi].dC[0] >> 2);
+            const int64_t rs = plan.g[gi].dC[0] >> 2;   // float4s per destination row
+#pragma unroll
+            for (int ee = 0; ee < 32; ++ee)
+                if (ok >> ee & 1) d4[s_off[w][ee] * rs] = make_float4(tile[0][lane][ee], tile[1][lane][ee], tile[2][lane][ee], tile[3][lane][ee]);
+        } else {
+            for (int cc = 0; cc < gn; ++cc) {
+                const int64_t dC = plan.g[gi].dC[cc];
+                float *dp = plan.g[gi].dst[cc] + (int64_t)lane * dC;
+#pragma unroll
+                for (int ee = 0; ee < 32; ++ee)
+                    if (ok >> ee & 1) dp[s_off[w][ee] * dC] = tile[cc][lane][ee];
+            }
+        }
+    }
+}
+
 __global__ void k_zero_i32(int32_t *p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0;
@@ -516,11 +597,48 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
     int64_t *offsets = reinterpret_cast<int64_t *>(static_cast<char *>(ws) + (((size_t)(nb + 1) * sizeof(int32_t) + 7) & ~(size_t)7));
     k_len_block_sums<<<nb, SCAN_TPB, 0, st>>>(lengths, E, sums);
     k_len_offsets<<<nb, SCAN_TPB, 0, st>>>(lengths, E, sums, base, offsets, total);
-    const int tb = cdiv(E, 128);
-    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, obs_dim, buf_states, lengths, offsets, mem_states, capacity);
-    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, act_width, buf_actions, lengths, offsets, mem_actions, capacity);
-    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_rewards, lengths, offsets, mem_rewards, capacity);
-    k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_dones, lengths, offsets, mem_dones, capacity);
+    // pack the channels of the four fields into groups of <= 4 (a group of 4 aligned channels of one field is stored as float4)
+    XferPlan plan{};
+    struct Field { const float *src; float *dst; int C; } fields[4] = {
+        {buf_states, mem_states, obs_dim}, {buf_actions, mem_actions, act_width}, {buf_rewards, mem_rewards, 1}, {buf_dones, mem_dones, 1}};
+    bool fits = true;
+    XferGroup cur{};
+    auto flush = [&]() {
+        if (cur.n == 0) return;
+        if (plan.ngroups == XF_MAX_GROUPS) { fits = false; return; }
+        plan.g[plan.ngroups++] = cur;
+        cur = XferGroup{};
+    };
+    for (const Field &f : fields) {
+        PRL_REQUIRE(f.src && f.dst && f.C > 0, "prl_buffer_transfer: null field");
+        int c = 0;
+        if (f.C % 4 == 0 && ((uintptr_t)f.dst & 15) == 0) {
+            for (; c + 4 <= f.C; c += 4) {
+                flush();
+                for (int k = 0; k < 4; ++k) { cur.src[k] = f.src + (size_t)(c + k) * E; cur.dst[k] = f.dst + c + k; cur.sstride[k] = (int64_t)f.C * E; cur.dC[k] = f.C; }
+                cur.n = 4; cur.vec = 1;
+                flush();
+            }
+        }
+        for (; c < f.C; ++c) {
+            if (cur.n == 4) flush();
+            const int k = cur.n++;
+            cur.src[k] = f.src + (size_t)c * E; cur.dst[k] = f.dst + c; cur.sstride[k] = (int64_t)f.C * E; cur.dC[k] = f.C;
+        }
+    }
+    flush();
+    for (const Field &f : fields) fits = fits && ((uintptr_t)f.src & 15) == 0;
+    if (fits && E % 4 == 0) {
+        const size_t smem = (size_t)XF_WARPS * 4 * 32 * 33 * sizeof(float);
+        PRL_CUDA(cudaFuncSetAttribute(k_transfer_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_transfer_tiles<<<dim3(cdiv(E, 32), cdiv(cdiv(T_cap, 32), XF_WARPS)), XF_WARPS * 32, smem, st>>>(E, T_cap, plan, lengths, offsets, capacity);
+    } else {   // very wide observations / actions: one field at a time
+        const int tb = cdiv(E, 128);
+        k_transfer<<<tb, 128, 0, st>>>(E, T_cap, obs_dim, buf_states, lengths, offsets, mem_states, capacity);
+        k_transfer<<<tb, 128, 0, st>>>(E, T_cap, act_width, buf_actions, lengths, offsets, mem_actions, capacity);
+        k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_rewards, lengths, offsets, mem_rewards, capacity);
+        k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_dones, lengths, offsets, mem_dones, capacity);
+    }
     k_zero_i32<<<cdiv(E, 256), 256, 0, st>>>(lengths, E);
     return check_launch("k_transfer");
 }

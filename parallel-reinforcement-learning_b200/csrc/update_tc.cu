@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
               float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
-              int *__restrict__ status, TcOptimizer opt) {
+              int *__restrict__ status, TcOptimizer opt, int qpc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bars[6];          // MMA completion: actor forward, actor backward, critic dgrad, trunk wgrad, critic wgrad, critic forward
     __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
@@ -415,7 +415,10 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     D.X_mn = smem_desc(smem_u32(sX), 128, CHUNK);
     const uint32_t lane_base = D.tmem + ((uint32_t)(rq * 32) << 16);
     bool mma_ok = true;
-    const int64_t ntiles = (b + TC_ROWS - 1) / TC_ROWS;
+    // this CTA's rows: quarters [blockIdx.x * qpc, + myq), tile t = quarters 4t .. 4t+3 of them
+    const int64_t row_base = (int64_t)blockIdx.x * qpc * 32;
+    const int myq = (int)max((int64_t)0, min((int64_t)qpc, (b + 31) / 32 - (int64_t)blockIdx.x * qpc));
+    const int ntiles = (myq + 3) >> 2;
     uint32_t it = 0;
     double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
     const int P = L.total;
@@ -433,7 +436,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 
     if (is_mma_warp) {
         // =============================================================================== MMA-issue warp
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tile = 0; tile < ntiles; ++tile, ++it) {
             const uint32_t parity = it & 1;
             mma_ok &= mbar_wait(&sbar[0], parity);
             fence_after_sync();
@@ -468,13 +471,33 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         constexpr int XR = 8;   // observation values kept in registers (observ_dim > 8 reads the rest on demand)
         float xn[XR];
         {
-            const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS + r;
+            const int64_t row0 = row_base + r;
 #pragma unroll
-            for (int i = 0; i < XR; ++i) xn[i] = (row0 < b && i < O) ? __ldg(states + row0 * O + i) : 0.f;
+            for (int i = 0; i < XR; ++i) xn[i] = (rq < myq && row0 < b && i < O) ? __ldg(states + row0 * O + i) : 0.f;
         }
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tile = 0; tile < ntiles; ++tile, ++it) {
             const uint32_t parity = it & 1;
-            const int64_t row = tile * TC_ROWS + r;
+            const int64_t row = row_base + (int64_t)tile * TC_ROWS + r;
+            if (4 * tile + rq >= myq) {
+                // this warp's quarter lies past the CTA's rows (last tile only): zero operand rows, keep every hand-off
+                if (it > 0) mma_ok &= mbar_wait(&bars[3], parity ^ 1);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int pc = 0; pc < 3; ++pc) {
+                        *reinterpret_cast<uint4 *>(sF + pc * PIECE + (2 * q + c) * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4 *>(sDZ + pc * PIECE + (2 * q + c) * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+                    }
+                if (q == 0)
+                    for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
+                staged(&sbar[0]);
+                bar_compute();       // the live warps' partial-output exchange, actor
+                staged(&sbar[1]);
+                bar_compute();       // critic
+                staged(&sbar[2]);
+                staged(&sbar[3]);
+                continue;
+            }
             const bool live = row < b;
             const float *xrow = states + (live ? row : 0) * O;   // dead rows read row 0 and are masked
             const float xmask = live ? 1.f : 0.f;
@@ -482,9 +505,10 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 #pragma unroll
             for (int i = 0; i < XR; ++i) x[i] = xn[i];
             {
-                const int64_t rown = (tile + gridDim.x) * TC_ROWS + r;
+                const int64_t rown = row + TC_ROWS;
+                const bool nlive = 4 * (tile + 1) + rq < myq && rown < b;
 #pragma unroll
-                for (int i = 0; i < XR; ++i) xn[i] = (rown < b && i < O) ? __ldg(states + rown * O + i) : 0.f;
+                for (int i = 0; i < XR; ++i) xn[i] = (nlive && i < O) ? __ldg(states + rown * O + i) : 0.f;
             }
             const float adv_i = live ? __ldg(adv + row) : 0.f, old_i = live ? __ldg(old_logp + row) : 0.f;
             const float ret_i = live ? __ldg(returns + row) : 0.f;
@@ -916,12 +940,31 @@ k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int
     if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) add_loss_sums(loss_partials, nblocks, loss_out, rows, threadIdx.x);
 }
 
-static int tc_grid(int64_t b) {
+// Row split.  The minibatch is cut into 32-row quarters (one per row-quarter warp group); CTA c owns the TC_QPC consecutive
+// quarters from c * qpc on, i.e. floor(qpc / 4) full 128-row tiles and a last tile with qpc % 4 live quarters whose dead
+// warps skip the CUDA-core work.  With qpc = ceil(quarters / SMs) every SM finishes within one quarter-tile of the others
+// (65 536 rows on 148 SMs: 14 quarters = 3.5 tiles each, instead of 4 tiles on 68 CTAs and 3 on 80).
+static void tc_split(int64_t b, int *grid, int *qpc) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t ntiles = (b + TC_ROWS - 1) / TC_ROWS;
-    return (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
+    const int64_t nq = (b + 31) / 32;
+    int64_t q = (nq + sms - 1) / sms;
+    if (q < 4) q = 4;   // small minibatches: whole tiles on fewer CTAs
+    *qpc = (int)q;
+    const int64_t gr = (nq + q - 1) / q;
+    *grid = (int)(gr > 0 ? gr : 1);
+}
+// upper bound of the grid over every minibatch of at most b rows (the workspace is sized once for the largest one)
+static int tc_grid_max(int64_t b) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t nt = (b + TC_ROWS - 1) / TC_ROWS;
+    return (int)(nt < sms ? (nt > 0 ? nt : 1) : sms);
+}
+static size_t tc_ws_floats(const PolicyLayout &L, int grid) {
+    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + 16;
 }
 
 }  // namespace prl
@@ -936,8 +979,7 @@ int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim) {
 
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    const int grid = tc_grid(batch);
-    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + 16;
+    return tc_ws_floats(L, tc_grid_max(batch));
 }
 
 // shared launcher: gradient only (opt == nullptr: + separate reduction kernel) or fused optimiser step
@@ -950,9 +992,10 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
                 "%s: only discrete policies with observ_dim <= %d and action_dim <= %d (got continuous=%d O=%d A=%d)", who, TC_MAX_O,
                 TC_MAX_A, is_continuous, obs_dim, action_dim);
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    const int grid = tc_grid(b);
+    int grid, qpc;
+    tc_split(b, &grid, &qpc);
     const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
-    PRL_REQUIRE(ws_floats >= prl_update_tc_ws_floats(is_continuous, obs_dim, action_dim, b), "%s: workspace too small", who);
+    PRL_REQUIRE(ws_floats >= tc_ws_floats(L, grid), "%s: workspace too small", who);
     PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "%s: workspace must be 16-byte aligned", who);
     const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
     const size_t smem = tc_smem_bytes(L, NA);
@@ -977,7 +1020,7 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
         attr[0].val.cooperative = optp ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
         PRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
-                                    loss_partials, status, opt));
+                                    loss_partials, status, opt, qpc));
         return PRL_OK;
     };
     const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);

@@ -217,18 +217,53 @@ def test_gae_flat_random_segments_bit_exact(ops):
         assert np.array_equal(bits(got.cpu().numpy()), bits(want)), (N, p_done)
 
 
-def test_gae_columns_bit_exact_and_equal_to_flat(ops):
+def test_gae_flat_halo_windows_and_unaligned_views(ops):
+    """The flat kernel's corner cases: segments that end just inside a 1 024-element chunk and reach back through the
+    128-element halo and further windows, equal-length episodes (the C2 / C3 shapes), arrays that are not 16-byte
+    aligned (scalar staging path) and a non-unit last done."""
+    rng = np.random.default_rng(12)
+    cases = []
+    for T, n in [(128, 300), (200, 200), (500, 33), (1, 3000), (1025, 7), (3000, 3)]:   # equal-length episodes
+        N = T * n
+        d = np.zeros(N, np.float32); d[T - 1::T] = 1.0
+        cases.append((N, d))
+    lens = rng.integers(1, 400, 500)                                                  # ragged episodes
+    d = np.zeros(int(lens.sum()), np.float32); d[np.cumsum(lens) - 1] = 1.0
+    cases.append((d.size, d))
+    d = np.zeros(5000, np.float32); d[[1023, 1024, 1025, 2047, 2048 + 127, 2048 + 128, 4095]] = 1.0   # ends on chunk / halo edges
+    cases.append((d.size, d))
+    for N, d in cases:
+        r = rng.standard_normal(N).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
+        want = cref.gae(r, d, v, v[-1], 0.995, 0.95)
+        got = ops.gae(dev(r), dev(d), dev(v), 0.995, 0.95)
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), N
+        # the same data at a 4-byte offset from a 16-byte boundary
+        pad = lambda a: dev(np.concatenate([np.zeros(1, np.float32), a]))[1:]
+        got = ops.gae(pad(r), pad(d), pad(v), 0.995, 0.95)
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), ("unaligned", N)
+    # open last segment with an explicit bootstrap value
+    N = 2500
+    r = rng.standard_normal(N).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
+    d = np.zeros(N, np.float32); d[700] = 1.0
+    want = cref.gae(r, d, v, np.float32(0.37), 0.99, 0.9)
+    got = ops.gae(dev(r), dev(d), dev(v), 0.99, 0.9, next_value=dev(np.array([0.37], np.float32)))
+    assert np.array_equal(bits(got.cpu().numpy()), bits(want))
+
+
+@pytest.mark.parametrize("T,E", [(64, 5000), (128, 4099), (37, 30), (200, 1024)])
+def test_gae_columns_bit_exact_and_equal_to_flat(ops, T, E):
+    """Ring-buffered kernel (E % 4 == 0) and the plain one (any E), ragged and full-length columns."""
     rng = np.random.default_rng(3)
-    T, E = 64, 5000
-    lens = rng.integers(1, T + 1, E).astype(np.int32)
-    r = rng.standard_normal((T, E)).astype(np.float32); v = rng.standard_normal((T, E)).astype(np.float32)
-    d = np.zeros((T, E), np.float32)
-    d[lens - 1, np.arange(E)] = 1.0
-    got = ops.gae_columns(dev(r), dev(d), dev(v), dev(lens), 0.995, 0.95).cpu().numpy()
-    for e in range(0, E, 97):
-        L = lens[e]
-        want = cref.gae(r[:L, e], d[:L, e], v[:L, e], v[L - 1, e], 0.995, 0.95)
-        assert np.array_equal(bits(got[:L, e]), bits(want))
+    for full in (False, True):
+        lens = np.full(E, T, np.int32) if full else rng.integers(1, T + 1, E).astype(np.int32)
+        r = rng.standard_normal((T, E)).astype(np.float32); v = rng.standard_normal((T, E)).astype(np.float32)
+        d = np.zeros((T, E), np.float32)
+        d[lens - 1, np.arange(E)] = 1.0
+        got = ops.gae_columns(dev(r), dev(d), dev(v), dev(lens), 0.995, 0.95).cpu().numpy()
+        for e in list(range(0, E, 97)) + [E - 1]:
+            L = lens[e]
+            want = cref.gae(r[:L, e], d[:L, e], v[:L, e], v[L - 1, e], 0.995, 0.95)
+            assert np.array_equal(bits(got[:L, e]), bits(want)), (T, E, e)
 
 
 def test_adv_normalize_matches_oracle(ops):
