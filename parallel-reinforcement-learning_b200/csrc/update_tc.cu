@@ -267,7 +267,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nbl
 }
 
 // sum over the CTAs' partial rows of parameter i, slice sl of RED_SL (blocks sl, sl + RED_SL, ... in ascending order)
-constexpr int RED_SL = 16, RED_MAX = 10;
+constexpr int RED_SL = 16, RED_MAX = 10;   // (8 x 19 would be one L2 round trip, but 19 live loads per thread spill: measured)
 __device__ __forceinline__ float reduce_slice(const float *__restrict__ partials, int nblocks, int stride, int i, int sl) {
     float s = 0.f;
     for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
@@ -731,36 +731,38 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         if (it > 0) mma_ok &= mbar_wait(&bars[3], (it - 1) & 1);
         fence_after_sync();
         TC_STAMP(14);
-        float *scratch = reinterpret_cast<float *>(sF);   // [128][68] fp32 = 34 KB inside the 48 KB F region, free now
+        // DW_h: lanes 0..63 hold the first piece window's products, lanes 64..127 the second's; thread (r, q) reads 16 columns
+        // of both heads and of DW0, parks them in shared memory (F and DZ regions, free now), then the CTA writes
+        // dW = first + second with coalesced stores.  One pass: all three tensor-memory loads in flight, two barriers.
         constexpr int SS = HID + 4;
-        // DW_h: lanes 0..63 hold the first piece window's products, lanes 64..127 the second's; thread (r, q) reads 16 columns,
-        // parks them in shared memory, then the CTA writes dW1_h = first + second with coalesced stores
-        for (int h = 0; h < 2; ++h) {
-            float v[TC_W];
-            tmem_ld16w(lane_base + TM_DW + 64 * h + j0, v);
-            bar_compute();
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<float4 *>(scratch + r * SS + j0 + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            bar_compute();
-            float *dst = part + L.head[h].w1;
-            for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
-                const int j = idx >> 6, k = idx & 63;
-                dst[idx] = (it > 0) ? scratch[j * SS + k] + scratch[(64 + j) * SS + k] : 0.f;
-            }
-        }
+        float *scratch0 = reinterpret_cast<float *>(sF);              // [128][68] fp32 = 34 KB inside the 48 KB F region
+        float *scratch1 = reinterpret_cast<float *>(sDZ);             // same, inside the 64 KB DZ region
+        float *scratch2 = scratch1 + TC_ROWS * SS;                    // [128][17] for DW0
         {
-            float v[TC_W];
-            tmem_ld16w(lane_base + TM_DW0, v);
-            bar_compute();
+            float v0[TC_W], v1[TC_W], v2[TC_W];
+            tmem_ld16(lane_base + TM_DW + j0, v0);
+            tmem_ld16(lane_base + TM_DW + 64 + j0, v1);
+            tmem_ld16(lane_base + TM_DW0, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                *reinterpret_cast<float4 *>(scratch0 + r * SS + j0 + 4 * k) = make_float4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3]);
+                *reinterpret_cast<float4 *>(scratch1 + r * SS + j0 + 4 * k) = make_float4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]);
+            }
             if (q == 0) {
 #pragma unroll
-                for (int i = 0; i < TC_W; ++i) scratch[r * 17 + i] = v[i];
+                for (int i = 0; i < TC_W; ++i) scratch2[r * 17 + i] = v2[i];
             }
             bar_compute();
+            float *dst0 = part + L.head[0].w1, *dst1 = part + L.head[1].w1;
+            for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
+                const int j = idx >> 6, k = idx & 63;
+                dst0[idx] = (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f;
+                dst1[idx] = (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f;
+            }
             for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
                 const int j = idx / O, i = idx - j * O;
-                part[L.w0 + idx] = (it > 0) ? scratch[j * 17 + i] + scratch[(64 + j) * 17 + i] : 0.f;
+                part[L.w0 + idx] = (it > 0) ? scratch2[j * 17 + i] + scratch2[(64 + j) * 17 + i] : 0.f;
             }
         }
         // column-sum accumulators (already in s_red / b2s): combine the four row quarters
@@ -868,7 +870,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             const int nc = min(RC, n_i - c0);
             if (tid < nc) {
                 float g = 0.f;
-                for (int rr = 0; rr < opt.world; ++rr) g += ld_relaxed_sys(opt.peers[rr] + goff + i0 + c0 + tid);
+                for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 peer loads in flight, summed in rank order
+                    float pv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pv[u] = r0 + u < opt.world ? ld_relaxed_sys(opt.peers[r0 + u] + goff + i0 + c0 + tid) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (r0 + u < opt.world) g += pv[u];
+                }
                 opt.grad[i0 + c0 + tid] = g;
                 sq[tid] = (double)g * g;
             }
@@ -919,9 +928,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     TC_SPAN(3);
 }
 
-// grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x 16 block slices per
-// CTA; slice sl adds blocks sl, sl+16, ... (<= 10 independent loads in flight per thread for <= 160 blocks), and the
-// sixteen slice sums are combined in a fixed tree.  loss_out += block loss partials.  (Separate-kernel form of the fused
+// grad[i] = sum over blocks of partials[b][i] in a fixed order (bit-reproducible): 64 parameters x RED_SL block slices per
+// CTA; slice sl adds blocks sl, sl + RED_SL, ... (RED_MAX independent loads in flight per thread), and the slice sums are
+// combined in a fixed tree.  loss_out += block loss partials.  (Separate-kernel form of the fused
 // tail above: used when the gradient is needed on its own, e.g. for the allreduce of the sharded path.)
 __global__ void __launch_bounds__(64 * RED_SL)
 k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int stride, float *__restrict__ grad,
