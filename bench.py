@@ -284,8 +284,15 @@ def run_b200(args):
         g = per[gk]
         rows_epochs = n_prof / world * args.k_epochs           # sample-epochs this rank pushed through the update kernel
         tf = rows_epochs * FLOPS_PER_SAMPLE_EPOCH / (g["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")   # dram__bytes_read + write of one launch (ncu --set full capture)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         roof = {"kernel": kernel_names[gk], "bound": "tensor", "achieved": tf,
-                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"], "traffic": None,
+                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (65 536 rows: 2.1 MB of row inputs + 36 KB of parameters are the algorithmic bytes)",
+                "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
                 "share_of_step": g["ms"] / ms_prof,

@@ -168,8 +168,13 @@ class PPO:
 
         if self.use_RND:  # PPO.py:157-178: rewards + intrinsic, THEN one predictor pass over the same chunks
             rewards = self.rnd.intrinsic_reward_device(states, add_to=rewards, out=R["rewards"][:N])
-            for i in range(0, N, mb):
-                self.rnd.update_pred_chunk(states[i:i + mb])
+            if comm is None:
+                for i in range(0, N, mb):
+                    self.rnd.update_pred_chunk(states[i:i + mb])
+            else:   # global chunk k = union of every rank's k-th local chunk, as for the policy minibatches below
+                mb_r, n_r, counts_r = pdist.minibatch_schedule(n_all, mb)
+                for k in range(n_r):
+                    self.rnd.update_pred_chunk(states[min(k * mb_r, N):min((k + 1) * mb_r, N)], comm=comm, global_rows=counts_r[k])
         self.memory.clear()  # PPO.py:184 (the device rows stay valid until the next transfer)
 
         # next_value = V(last stored state), PPO.py:188

@@ -75,12 +75,21 @@ class RND(nn.Module):
         return t.cat([self.intrinsic_reward_device(self._chunk(v)) for v in values], dim=0)
 
     @t.no_grad()
-    def update_pred_chunk(self, states: t.Tensor):
+    def update_pred_chunk(self, states: t.Tensor, comm=None, global_rows: int | None = None):
+        """One MSE(mean) + AdamW step on `states`.  Sharded (`comm`): this rank's rows are its part of a global chunk of
+        `global_rows` rows - the local mean-gradient is re-weighted by n / global_rows and summed over the ranks (one
+        allreduce of the flat predictor gradient), so every rank applies the same step to its replica."""
         n = states.shape[0]
-        need = ops.update_ws_floats(False, self.in_features, self.out_features, n) + 4096
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = t.empty(need, dtype=t.float32, device=self.device)
-        ops.rnd_grad(self.target_flat, self.pred_flat, self.in_features, self.out_features, states, self._grad, self._loss, self._ws)
+        if n > 0:
+            need = ops.update_ws_floats(False, self.in_features, self.out_features, n) + 4096
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = t.empty(need, dtype=t.float32, device=self.device)
+            ops.rnd_grad(self.target_flat, self.pred_flat, self.in_features, self.out_features, states, self._grad, self._loss, self._ws)
+        else:
+            self._grad.zero_()
+        if comm is not None:
+            self._grad.mul_(n / float(global_rows))
+            comm.allreduce_(self._grad)
         self.optimizer.step(self._grad)
 
     def update_pred(self, values) -> None:

@@ -41,5 +41,20 @@ for graph in (False, True):
     both = [t.empty_like(got) for _ in range(2)]
     t.distributed.all_gather(both, got)
     assert t.equal(both[0], both[1]), "ranks diverged"
+# Acrobot + RND, sharded: the predictor update allreduces its re-weighted gradient, so the replicas stay identical
+t.manual_seed(7)
+ppo = PPO(is_continuous=False, observ_dim=6, action_dim=3, lr=3e-4, k_epochs=2, mini_batch_size=2048, batch_size=256, use_RND=True, beta=0.001)
+ppo.show_progress = False
+pred0 = ppo.rnd.pred_flat.clone()
+t.manual_seed(5 + rank)
+a = AsyncPPO(env=make("Acrobot-v1", max_episode_steps=64), ppo=ppo, num_envs=48 if rank == 0 else 16, steps=10**9)
+a.worker()
+ppo.learn()
+t.cuda.synchronize()
+for flat in (ppo.rnd.pred_flat, ppo.policy.flat):
+    both = [t.empty_like(flat) for _ in range(2)]
+    t.distributed.all_gather(both, flat.contiguous())
+    assert t.equal(both[0], both[1]), "RND run: ranks diverged"
+assert not t.equal(pred0, ppo.rnd.pred_flat) and t.isfinite(ppo.rnd.pred_flat).all()
 open(os.path.join(out, f"rank{rank}"), "w").write("ok")
 t.distributed.destroy_process_group()
