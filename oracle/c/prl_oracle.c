@@ -23,13 +23,14 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { ORC_CARTPOLE = 0, ORC_PENDULUM = 1, ORC_ACROBOT = 2 };
+enum { ORC_CARTPOLE = 0, ORC_PENDULUM = 1, ORC_ACROBOT = 2, ORC_MOUNTAINCAR = 3 };
 
 int orc_env_dims(int env, int *S, int *O, int *A, int *cont, int *max_steps) {
     switch (env) {
     case ORC_CARTPOLE: *S = 4; *O = 4; *A = 2; *cont = 0; *max_steps = 500; return 0;
     case ORC_PENDULUM: *S = 2; *O = 3; *A = 1; *cont = 1; *max_steps = 200; return 0;
     case ORC_ACROBOT:  *S = 4; *O = 6; *A = 3; *cont = 0; *max_steps = 500; return 0;
+    case ORC_MOUNTAINCAR: *S = 2; *O = 2; *A = 3; *cont = 0; *max_steps = 200; return 0;
     }
     return -1;
 }
@@ -155,10 +156,33 @@ static int acrobot_step(double *s, int action, float *obs, double *reward) {
     return terminated;
 }
 
+/* ---------------------------------------------------------------- MountainCar-v0 */
+static void mountaincar_obs(const double *s, float *o) {
+    o[0] = (float)s[0];
+    o[1] = (float)s[1];
+}
+
+static int mountaincar_step(double *s, int action, float *obs, double *reward) {
+    const double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, goal_velocity = 0.0;
+    const double force = 0.001, gravity = 0.0025;
+    double position = s[0], velocity = s[1];
+    velocity += (double)(action - 1) * force + cos(3 * position) * (-gravity);
+    velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+    position += velocity;
+    position = position < min_position ? min_position : (position > max_position ? max_position : position);
+    if (position == min_position && velocity < 0) velocity = 0;
+    s[0] = position;
+    s[1] = velocity;
+    mountaincar_obs(s, obs);
+    *reward = -1.0;
+    return position >= goal_position && velocity >= goal_velocity;
+}
+
 /* ---------------------------------------------------------------- dispatch */
 void orc_env_obs(int env, const double *state, float *obs) {
     if (env == ORC_CARTPOLE) cartpole_obs(state, obs);
     else if (env == ORC_PENDULUM) pendulum_obs(state, obs);
+    else if (env == ORC_MOUNTAINCAR) mountaincar_obs(state, obs);
     else acrobot_obs(state, obs);
 }
 
@@ -166,6 +190,7 @@ void orc_env_obs(int env, const double *state, float *obs) {
 int orc_env_step(int env, double *state, const void *action, float *obs, double *reward) {
     if (env == ORC_CARTPOLE) return cartpole_step(state, *(const int32_t *)action, obs, reward);
     if (env == ORC_PENDULUM) return pendulum_step(state, (const float *)action, obs, reward);
+    if (env == ORC_MOUNTAINCAR) return mountaincar_step(state, *(const int32_t *)action, obs, reward);
     return acrobot_step(state, *(const int32_t *)action, obs, reward);
 }
 

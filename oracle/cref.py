@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
-ENV_CODES = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2}
+ENV_CODES = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3}
 
 
 def build(force: bool = False) -> str:

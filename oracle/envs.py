@@ -8,6 +8,7 @@ This file restates its *published* classic-control algorithms from memory:
   gymnasium/envs/classic_control/cartpole.py   (CartPoleEnv.step/reset)
   gymnasium/envs/classic_control/pendulum.py   (PendulumEnv.step/reset, angle_normalize)
   gymnasium/envs/classic_control/acrobot.py    (AcrobotEnv.step/_dsdt, rk4, wrap, bound)
+  gymnasium/envs/classic_control/mountain_car.py (MountainCarEnv.step/reset)
   gymnasium/wrappers/common.py                 (TimeLimit)
 
 PARITY UNPINNED against gymnasium itself: there is no gymnasium source, wheel or golden vector to
@@ -29,7 +30,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-__all__ = ["make", "CartPole", "Pendulum", "Acrobot", "ENV_IDS"]
+__all__ = ["make", "CartPole", "Pendulum", "Acrobot", "MountainCar", "ENV_IDS"]
 
 
 class _Space(SimpleNamespace):
@@ -276,7 +277,45 @@ class Acrobot(_BaseEnv):
         return self._obs(), reward, terminated
 
 
-ENV_IDS = {"CartPole-v1": CartPole, "Pendulum-v1": Pendulum, "Acrobot-v1": Acrobot}
+class MountainCar(_BaseEnv):
+    """gymnasium/envs/classic_control/mountain_car.py::MountainCarEnv (restated from memory, like the others)."""
+
+    env_id = "MountainCar-v0"
+    default_max_episode_steps = 200
+
+    def __init__(self, max_episode_steps=None, goal_velocity=0):
+        super().__init__(max_episode_steps)
+        self.min_position = -1.2
+        self.max_position = 0.6
+        self.max_speed = 0.07
+        self.goal_position = 0.5
+        self.goal_velocity = goal_velocity
+        self.force = 0.001
+        self.gravity = 0.0025
+        self.observation_space = _Space(shape=(2,), dtype=np.float32)
+        self.action_space = _Space(n=3, shape=(), dtype=np.int64)
+
+    def _draw_state(self):
+        return np.array([self.np_random.uniform(low=-0.6, high=-0.4), 0])
+
+    def _obs(self):
+        return np.array(self.state, dtype=np.float32)
+
+    def _physics(self, action):
+        position, velocity = self.state
+        velocity += (action - 1) * self.force + math.cos(3 * position) * (-self.gravity)
+        velocity = np.clip(velocity, -self.max_speed, self.max_speed)
+        position += velocity
+        position = np.clip(position, self.min_position, self.max_position)
+        if position == self.min_position and velocity < 0:
+            velocity = 0
+        terminated = bool(position >= self.goal_position and velocity >= self.goal_velocity)
+        reward = -1.0
+        self.state = (position, velocity)
+        return self._obs(), reward, terminated
+
+
+ENV_IDS = {"CartPole-v1": CartPole, "Pendulum-v1": Pendulum, "Acrobot-v1": Acrobot, "MountainCar-v0": MountainCar}
 
 
 def make(env_id: str, max_episode_steps: int | None = None):

@@ -3,7 +3,8 @@
 //
 // Reference call sites: /root/reference/AsyncTools/AsyncPPO.py:53 (env.reset) and :76 (env.step) inside
 // EnvVectorizer; the physics itself is gymnasium==1.1.1 classic_control (third-party):
-//   CartPoleEnv.step  Euler, tau 0.02;  PendulumEnv.step  float32 torque entering fp64;  AcrobotEnv.step  RK4 "book".
+//   CartPoleEnv.step  Euler, tau 0.02;  PendulumEnv.step  float32 torque entering fp64;  AcrobotEnv.step  RK4 "book";
+//   MountainCarEnv.step  clipped velocity / position updates.
 #pragma once
 #include "common.cuh"
 #include "pow_glibc.cuh"
@@ -23,7 +24,9 @@ struct CartPole {
     static constexpr bool CONT = false;
     using Action = int;
     __host__ __device__ static constexpr double reset_hi(int) { return 0.05; }   // reset: U(-0.05, 0.05)^4
+    __host__ __device__ static constexpr double reset_lo(int) { return -0.05; }
     static constexpr bool RESET_F32 = false;
+    static constexpr int RESET_DRAWS = S;   // state components drawn at reset (the rest start at 0)
 
     __device__ static __forceinline__ void obs(const double (&s)[S], float (&o)[O]) {
 #pragma unroll
@@ -56,7 +59,9 @@ struct Pendulum {
     static constexpr bool CONT = true;
     using Action = float;
     __host__ __device__ static constexpr double reset_hi(int i) { return i == 0 ? 3.141592653589793 : 1.0; }  // U(-[pi,1], [pi,1])
+    __host__ __device__ static constexpr double reset_lo(int i) { return i == 0 ? -3.141592653589793 : -1.0; }
     static constexpr bool RESET_F32 = false;
+    static constexpr int RESET_DRAWS = S;
 
     __device__ static __forceinline__ void obs(const double (&s)[S], float (&o)[O]) {
         o[0] = (float)cos_glibc(s[0]);
@@ -92,7 +97,9 @@ struct Acrobot {
     static constexpr bool CONT = false;
     using Action = int;
     __host__ __device__ static constexpr double reset_hi(int) { return 0.1; }   // reset: U(-0.1, 0.1)^4
+    __host__ __device__ static constexpr double reset_lo(int) { return -0.1; }
     static constexpr bool RESET_F32 = true;  // gymnasium casts the drawn state to float32
+    static constexpr int RESET_DRAWS = S;
 
     __device__ static __forceinline__ void obs(const double (&s)[S], float (&o)[O]) {
         o[0] = (float)cos_glibc(s[0]);
@@ -156,6 +163,37 @@ struct Acrobot {
     }
 };
 
+// MountainCar-v0 (gymnasium/envs/classic_control/mountain_car.py): state (position, velocity) as python floats.
+struct MountainCar {
+    static constexpr int ID = PRL_ENV_MOUNTAINCAR, S = 2, O = 2, A = 3, AS = 1, MAX_STEPS = 200;
+    static constexpr bool CONT = false;
+    using Action = int;
+    __host__ __device__ static constexpr double reset_hi(int) { return -0.4; }   // reset: position U(-0.6, -0.4), velocity 0
+    __host__ __device__ static constexpr double reset_lo(int) { return -0.6; }
+    static constexpr bool RESET_F32 = false;
+    static constexpr int RESET_DRAWS = 1;
+
+    __device__ static __forceinline__ void obs(const double (&s)[S], float (&o)[O]) {
+        o[0] = (float)s[0];
+        o[1] = (float)s[1];
+    }
+    __device__ static __forceinline__ bool step(double (&s)[S], int action, double &reward) {
+        constexpr double min_position = -1.2, max_position = 0.6, max_speed = 0.07, goal_position = 0.5, goal_velocity = 0.0;
+        constexpr double force = 0.001, gravity = 0.0025;
+        double position = s[0], velocity = s[1];
+        // velocity += (action - 1) * force + cos(3 * position) * (-gravity)
+        velocity = dadd(velocity, dadd(dmul((double)(action - 1), force), dmul(cos_glibc(dmul(3.0, position)), -gravity)));
+        velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+        position = dadd(position, velocity);
+        position = position < min_position ? min_position : (position > max_position ? max_position : position);
+        if (position == min_position && velocity < 0) velocity = 0.0;
+        s[0] = position;
+        s[1] = velocity;
+        reward = -1.0;
+        return position >= goal_position && velocity >= goal_velocity;
+    }
+};
+
 // dispatch a functor templated on the env type
 template <typename F>
 inline int dispatch_env(int env_id, F &&f) {
@@ -163,6 +201,7 @@ inline int dispatch_env(int env_id, F &&f) {
         case PRL_ENV_CARTPOLE: return f(CartPole{});
         case PRL_ENV_PENDULUM: return f(Pendulum{});
         case PRL_ENV_ACROBOT: return f(Acrobot{});
+        case PRL_ENV_MOUNTAINCAR: return f(MountainCar{});
     }
     set_error("unknown env id %d", env_id);
     return PRL_ERR_INVALID;

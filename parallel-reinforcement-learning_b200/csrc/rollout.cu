@@ -42,10 +42,11 @@ __global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__re
     uint32_t r[4];
 #pragma unroll
     for (int i = 0; i < ENV::S; ++i) {
+        if (i >= ENV::RESET_DRAWS) { s[i] = 0.0; continue; }
         if ((i & 1) == 0) ph((uint32_t)e, (uint32_t)episode, (STREAM_RESET << 24) | (uint32_t)(i >> 1), (uint32_t)(episode >> 32), r);
         const double u = u01d(r[2 * (i & 1)], r[2 * (i & 1) + 1]);
         // numpy Generator.uniform: low + (high - low) * u
-        const double hi = ENV::reset_hi(i), lo = -hi;
+        const double hi = ENV::reset_hi(i), lo = ENV::reset_lo(i);
         double v = dadd(lo, dmul(dsub(hi, lo), u));
         if (ENV::RESET_F32) v = (double)(float)v;
         s[i] = v;

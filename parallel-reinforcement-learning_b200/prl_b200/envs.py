@@ -12,6 +12,7 @@ _SPECS = {
     "CartPole-v1": dict(S=4, O=4, A=2, continuous=False, max_steps=500),
     "Pendulum-v1": dict(S=2, O=3, A=1, continuous=True, max_steps=200),
     "Acrobot-v1": dict(S=4, O=6, A=3, continuous=False, max_steps=500),
+    "MountainCar-v0": dict(S=2, O=2, A=3, continuous=False, max_steps=200),
 }
 
 

@@ -77,6 +77,8 @@ def initial_states(env_id, E, rng):
     if env_id == "Pendulum-v1":
         hi = np.array([np.pi, 1.0])
         return rng.uniform(-hi, hi, size=(E, 2))
+    if env_id == "MountainCar-v0":   # wider than gymnasium's reset (-0.6..-0.4, 0) so that goals and the left wall are reached
+        return rng.uniform([-1.2, -0.07], [0.55, 0.07], size=(E, 2))
     return rng.uniform(-0.1, 0.1, size=(E, 4)).astype(np.float32).astype(np.float64)
 
 
@@ -258,6 +260,11 @@ def gen_utils(ref_async, ref_utils, seed):
 def main():
     ref_async, ref_utils, ref_ppo = import_reference()
     t.set_num_threads(1)
+    if "--only-mountaincar" in sys.argv:   # added after the other fixtures were frozen
+        v = gen_rollout(ref_async, "MountainCar-v0", E=16, T=60, seed=14)
+        np.savez_compressed(os.path.join(HERE, "rollout_mountaincar.npz"), **v)
+        print("mountaincar N =", len(v["states"]), "steps", v["nsteps"], "reward", float(v["reward_score"]), "goals", int((v["dones"] > 0).sum()))
+        return
     rolls = {
         "cartpole": gen_rollout(ref_async, "CartPole-v1", E=12, T=40, seed=11),
         "pendulum": gen_rollout(ref_async, "Pendulum-v1", E=6, T=25, seed=12),

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import cref, ppo as oppo  # noqa: E402
 
-ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1"}
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0"}
 
 
 @pytest.fixture(scope="module")
@@ -205,7 +205,7 @@ def test_stepwise_api_reproduces_reference_worker_trace(api, golden, key):
     assert np.array_equal(bits(env.sim.get_state().cpu().numpy()), bits(g["final_state"]))
 
 
-@pytest.mark.parametrize("key,cont", [("cartpole", False), ("pendulum", True), ("acrobot", False)])
+@pytest.mark.parametrize("key,cont", [("cartpole", False), ("pendulum", True), ("acrobot", False), ("mountaincar", False)])
 def test_fused_worker_equals_stepwise_worker(api, key, cont):
     """AsyncPPO.worker(): the one-launch fused rollout and the step-by-step loop (PPO.get_action -> EnvVectorizer.step ->
     utils.*) draw the same Philox numbers and must fill ppo.memory identically (bit-exact), sampled actions included."""

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import cref, ppo as oppo  # noqa: E402
 
-ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1"}
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0"}
 
 
 @pytest.fixture(scope="module")
@@ -132,7 +132,7 @@ def test_fused_rollout_matches_reference_worker_golden(ops, golden, key):
     assert r["scores"][0] == pytest.approx(float(g["reward_score"]), rel=1e-12)
 
 
-@pytest.mark.parametrize("key,E,T", [("cartpole", 4096, 128), ("pendulum", 2048, 200), ("acrobot", 1024, 120)])
+@pytest.mark.parametrize("key,E,T", [("cartpole", 4096, 128), ("pendulum", 2048, 200), ("acrobot", 1024, 120), ("mountaincar", 4096, 200)])
 def test_fused_rollout_matches_c_oracle(ops, key, E, T):
     env_id = ENVS[key]
     rng = np.random.default_rng(42)
@@ -141,6 +141,8 @@ def test_fused_rollout_matches_c_oracle(ops, key, E, T):
         s0 = rng.uniform(-0.05, 0.05, (E, 4)); tape = rng.integers(0, 2, (T, E)).astype(np.int32)
     elif key == "pendulum":
         s0 = rng.uniform([-np.pi, -1], [np.pi, 1], (E, 2)); tape = (2 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
+    elif key == "mountaincar":   # start states over the whole track so that goals and the left wall are hit
+        s0 = rng.uniform([-1.2, -0.07], [0.55, 0.07], (E, 2)); tape = rng.integers(0, 3, (T, E)).astype(np.int32)
     else:
         s0 = rng.uniform(-0.1, 0.1, (E, 4)).astype(np.float32).astype(np.float64); tape = rng.integers(0, 3, (T, E)).astype(np.int32)
     want = cref.rollout(env_id, s0, tape, T)
@@ -457,3 +459,74 @@ def test_rnd_intrinsic_and_grad_match_reference(ops, golden):
         ops.adamw_step(pp, grad, m, v, step, 1e-3, max_norm=0.0)
     want = np.concatenate([g[f"rnd_post.pred_net.{k}"].ravel() for k in oppo.RND_KEYS])
     np.testing.assert_allclose(pp.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ full BASELINE sizes
+def test_full_size_c2_properties(ops):
+    """configs[1] at full size (CartPole, 65 536 envs x T = 128, ~1.5 M ragged transitions with a taped random policy):
+    too large for the oracle, so the kernels are tied together by size-independent properties -
+    a sampled chunk of envs against the plain-C oracle, the rollout repeated bit for bit, transfer conservation laws,
+    flat GAE == column GAE bit for bit, sortedness of the env-major order, advantage statistics."""
+    E, T = 65536, 128
+    rng = np.random.default_rng(2024)
+    s0 = rng.uniform(-0.05, 0.05, (E, 4))
+    tape = rng.integers(0, 2, (T, E)).astype(np.int32)
+
+    def roll():
+        sim = ops.EnvState("CartPole-v1", E, T)
+        sim.set_state(dev(s0))
+        buf = ops.RolloutBuffer(E, T, 4, 1)
+        scores = t.zeros(2, dtype=t.float64, device="cuda")
+        ops.rollout(sim, buf, None, 1.0, 0, 0, scores, tape=dev(tape))
+        return sim, buf, scores
+
+    sim, buf, scores = roll()
+    _, buf2, _ = roll()
+    lens = buf.lengths.clone()
+    live = (t.arange(T, device="cuda")[:, None] < lens[None, :])                     # [T][E] slots that hold a transition
+    for a, b in ((buf.states, buf2.states), (buf.actions, buf2.actions)):
+        m = live[:, None, :].expand_as(a)
+        assert t.equal(a[m], b[m])                                                    # idempotence: same inputs, same bits
+    assert t.equal(buf.rewards[live], buf2.rewards[live]) and t.equal(lens, buf2.lengths)
+    N = int(lens.sum().item())
+    assert N == int(scores[1].item()) and lens.min().item() >= 1 and lens.max().item() <= T
+    # a slice of envs against the oracle (the kernel treats every env alike)
+    sl = slice(1000, 1256)
+    want = cref.rollout("CartPole-v1", s0[sl], np.ascontiguousarray(tape[:, sl]), T)
+    assert np.array_equal(lens[sl].cpu().numpy(), want["lengths"])
+    # done flags: exactly one per env, at its last step
+    assert int(buf.dones[live].sum().item()) == E
+    assert t.equal(buf.dones[(lens - 1).long(), t.arange(E, device="cuda")], t.ones(E, device="cuda"))
+    # column GAE on the time-major buffer
+    v_tm = t.rand(T, E, device="cuda")
+    ret_tm = ops.gae_columns(buf.rewards, buf.dones, v_tm, lens, 0.995, 0.95)
+    # transfer: time-major -> env-major; values ride along as a fake 1-channel "action" field of a second buffer view
+    ms = t.empty(N, 4, device="cuda"); ma = t.empty(N, 1, device="cuda"); mr = t.empty(N, device="cuda"); md = t.empty(N, device="cuda")
+    total = t.zeros(1, dtype=t.int64, device="cuda")
+    vbuf = ops.RolloutBuffer(E, T, 4, 1)
+    vbuf.states.copy_(buf.states); vbuf.actions.copy_(v_tm.view(T, 1, E)); vbuf.rewards.copy_(ret_tm); vbuf.dones.copy_(buf.dones)
+    vbuf.lengths.copy_(lens)
+    buf.transfer(ms, ma, mr, md, 0, total)
+    assert int(total.item()) == N and int(buf.lengths.sum().item()) == 0
+    mv = t.empty(N, 1, device="cuda"); mret = t.empty(N, device="cuda"); ms2 = t.empty(N, 4, device="cuda"); md2 = t.empty(N, device="cuda")
+    vbuf.transfer(ms2, mv, mret, md2, 0, total)
+    assert t.equal(ms, ms2) and t.equal(md, md2)
+    # conservation: every field keeps its multiset of values (checksums in float64 are order-independent enough: exact for 0/1 data)
+    assert float(mr.double().sum().item()) == float(buf.rewards[live].double().sum().item()) == float(N)   # CartPole: reward 1 per step
+    assert int(md.sum().item()) == E and float(md[-1].item()) == 1.0
+    assert float(ma.double().sum().item()) == float(buf.actions[:, 0, :][live].double().sum().item())
+    # env-major order: episode e occupies rows [off_e, off_e + len_e) and ends with its done flag
+    off = t.cumsum(lens.long(), 0) - lens.long()
+    assert t.equal(md[(off + lens.long() - 1)], t.ones(E, device="cuda"))
+    assert t.equal(ms[off], dev(s0.astype(np.float32)))                                # first stored state of env e = its start state
+    # flat GAE over the env-major buffer == column GAE over the time-major one, bit for bit
+    ret_flat = ops.gae(mr, md, mv.view(-1), 0.995, 0.95)
+    assert t.equal(ret_flat, mret)
+    # and the sampled envs against the oracle's flat scan
+    lo, hi = int(off[sl.start].item()), int(off[sl.stop].item())
+    vs = mv.view(-1)[lo:hi].cpu().numpy()
+    w = cref.gae(want["rewards"], want["dones"], vs, vs[-1], 0.995, 0.95)
+    assert np.array_equal(bits(ret_flat[lo:hi].cpu().numpy()), bits(w))
+    # advantage normalisation: zero mean, unit (unbiased) std
+    adv, _ = ops.adv_normalize(ret_flat, mv.view(-1).contiguous())
+    assert abs(float(adv.double().mean().item())) < 1e-4 and abs(float(adv.double().std().item()) - 1.0) < 1e-4

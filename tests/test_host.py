@@ -102,8 +102,10 @@ def test_env_descriptor_stands_in_for_gym_make():
         class spec:
             id, max_episode_steps = "Acrobot-v1", 500
     assert describe(FakeGym()).env_id == "Acrobot-v1"
+    m = prl_b200.make("MountainCar-v0")
+    assert m.observation_space.shape[0] == 2 and m.action_space.n == 3 and m.spec.max_episode_steps == 200
     with pytest.raises(ValueError):
-        prl_b200.make("MountainCar-v0")
+        prl_b200.make("LunarLander-v3")
 
 
 def test_shard_bounds_and_minibatch_schedule():

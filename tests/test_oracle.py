@@ -6,7 +6,7 @@ import torch as t
 
 from oracle import cref, envs as oenvs, ppo as oppo, vec as ovec
 
-ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1"}
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0"}
 
 
 def bits(a):
