@@ -243,6 +243,7 @@ class PPO:
             side = self._side_stream = getattr(self, "_side_stream", None) or t.cuda.Stream()
             side.wait_stream(t.cuda.current_stream())
             graph = t.cuda.CUDAGraph()
+            counts0 = dict(ops._lib.CALL_COUNTS)
             with t.cuda.stream(side):
                 graph.capture_begin()   # (torch.cuda.graph() would also synchronise, collect garbage and empty the allocator cache)
                 try:
@@ -251,10 +252,14 @@ class PPO:
                 finally:
                     graph.capture_end()
             t.cuda.current_stream().wait_stream(side)
+            captured = {k: v - counts0.get(k, 0) for k, v in ops._lib.CALL_COUNTS.items() if v != counts0.get(k, 0)}
             for _ in range(self.k_epochs):
                 graph.replay()   # AdamW's step number is device-resident, so every replay advances it
                 if pbar is not None:
                     pbar.update(N)
+            # launch accounting: the capture itself launched nothing, every replay launched all captured kernels
+            for k, v in captured.items():
+                ops._lib.CALL_COUNTS[k] += (self.k_epochs - 1) * v
             self.optimizer.step_count = first_step + steps
             graphs = graph
             self._graphs = graphs  # keep alive until the replays have run
