@@ -35,6 +35,9 @@ UNIT = "env-steps/s"
 # algorithmic FLOPs of one sample-epoch of the update, CartPole shapes: forward 2*(O*64 + 2*64^2 + 64*A
 # + 64) = 17 280, forward + backward ~ 3x
 FLOPS_PER_SAMPLE_EPOCH = 51_840.0
+# bf16 MMA flops the tensor-core kernel issues per row: forward 2 heads x 24 MMAs (128x64x16), dgrad 2 x 24, wgrad 2 x 32,
+# trunk wgrad 32 x (128x16x16), all x 2 flops, per 128-row tile
+EXECUTED_BF16_FLOPS_PER_ROW = (2 * 24 * 128 * 64 * 16 * 2 + 2 * 24 * 128 * 64 * 16 * 2 + 2 * 32 * 128 * 64 * 16 * 2 + 32 * 128 * 16 * 16 * 2) / 128.0
 
 
 def parse():
@@ -295,6 +298,12 @@ def run_b200(args):
                 "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
+                # what the tensor pipe really executes: every fp32-grade product is six bf16 MMAs (bf16x3 split) and the weight
+                # gradients run on stacked piece windows - 44.0 MFLOP of bf16 MMAs per 128-row tile
+                "executed_bf16_flops_per_sample_epoch": EXECUTED_BF16_FLOPS_PER_ROW,
+                "executed_bf16_tflops": tf * EXECUTED_BF16_FLOPS_PER_ROW / FLOPS_PER_SAMPLE_EPOCH,
+                "limiter": "CUDA-core epilogues (GroupNorm / SiLU / loss forward + backward, bf16x3 splitting, column sums): ncu issue slots 32 % "
+                           "busy with 4.25 warps per scheduler, tensor pipe 9 % active, DRAM 0.3 % (profiles/r01_ncu_summary_v2.txt)",
                 "share_of_step": g["ms"] / ms_prof,
                 "measured_on": "one launch-by-launch step after the timed region (the timed region replays CUDA graphs)"}
     hbm = {}
@@ -304,6 +313,12 @@ def run_b200(args):
             gbs = (n_prof / world) * b / (per[name]["ms"] * 1e-3) / 1e9
             hbm[name] = {"GB/s": gbs, "frac_of_" + pk["source"] + "_hbm": gbs / pk["hbm"], "bytes_per_transition": b, "ms": per[name]["ms"], "calls": per[name]["calls"]}
 
+    # the two forward-only kernels are bound by the fp32 FMA pipe, not by HBM: report their TFLOP/s
+    fma = {}
+    for name, fl in (("prl_rollout", 8960.0), ("prl_policy_evaluate", 17280.0)):
+        if name in per and per[name]["ms"] > 0:
+            fma[name] = {"TFLOP/s_fp32": (n_prof / world) * fl / (per[name]["ms"] * 1e-3) / 1e12, "flops_per_row": fl, "ms": per[name]["ms"],
+                         "fp32_fma_peak_TFLOP/s": 148 * 128 * 2 * 1.965e9 / 1e12}
     micro = hbm_microbench(pk) if rank == 0 else None
     if rank != 0:
         return
@@ -320,6 +335,7 @@ def run_b200(args):
         "clocks": clk,
         "roofline": roof,
         "hbm_kernels": hbm,
+        "fma_kernels": fma,
         "hbm_micro": micro,
         "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])},
     }
@@ -419,7 +435,23 @@ def hbm_microbench(pk, E=65536, T=128):
     taped(sims[0], bufs[0]); scores.zero_(); taped(sims[0], bufs[0])
     n_steps = float(scores.cpu()[1])
     ms = timeit([lambda s_=s_, b=b: taped(s_, b) for s_, b in zip(sims, bufs)])
-    out["rollout_taped_cartpole"] = {"GB/s": n_steps * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "env_steps": n_steps}
+    out["rollout_taped_cartpole"] = {"GB/s": n_steps * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "env_steps": n_steps,
+                                     "note": "65 536 envs = 14 warps per SM running ~22-step random-policy episodes of fp64 physics: latency-bound at this size"}
+    del sims, bufs
+    # the same at 2^20 envs (C5's range), where there are enough envs per SM for the buffer writes to matter
+    E3 = 1 << 20
+    sim3 = ops.EnvState("CartPole-v1", E3, T)
+    buf3 = ops.RolloutBuffer(E3, T, 4, 1)
+    tape3 = t.randint(0, 2, (T, E3), dtype=t.int32, device=dev)
+
+    def taped3():
+        sim3.reset(1, 1)
+        ops.rollout(sim3, buf3, None, 1.0, 0, 1, scores, tape=tape3)
+    scores.zero_(); taped3()
+    n3 = float(scores.cpu()[1])
+    ms = timeit([taped3] * 2, reps=3)
+    out["rollout_taped_cartpole_1M_envs"] = {"GB/s": n3 * 102 / ms / 1e6, "ms": ms, "bytes_per_env_step": 102, "env_steps": n3}
+    del sim3, buf3, tape3
     for k in out:
         out[k]["frac_of_" + pk["source"] + "_hbm"] = out[k]["GB/s"] / pk["hbm"]
     return out

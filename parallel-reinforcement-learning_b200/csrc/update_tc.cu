@@ -218,7 +218,7 @@ struct TcOptimizer {
     double *loss_out;                         // 4 doubles, accumulated
     double rows;
     // sharded runs: the gradient exchange happens inside this kernel over NVLink peer memory instead of an NCCL allreduce.
-    // peers[r] = base of rank r's exchange buffer {G[2][gstride] float (double-buffered by step parity), flags[world] u32}
+    // peers[r] = base of rank r's exchange buffer {inbox[2 (step parity)][world (sender)][gstride] float, flags[world][slices] u32}
     float *const *peers;
     int rank, world, gstride;
 };
@@ -811,81 +811,77 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const int nb = gridDim.x;
     if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
     TC_SPAN0(0);
-    const int S = (P + nb - 1) / nb, i0 = blockIdx.x * S, n_i = max(0, min(S, P - i0));   // 61 for P = 9 027 on 148 CTAs
-    constexpr int RC = 64;                                            // parameters reduced per pass
+    // The parameters are cut into slices of RC = 64 (142 slices for P = 9 027); CTA c owns slices c, c + nb, ...  The cut does
+    // not depend on the grid, so ranks whose minibatches have different row counts (different grids) agree on it.
+    constexpr int RC = 64;                                            // parameters per slice
+    const int nsl = (P + RC - 1) / RC;
     float *sl_part = reinterpret_cast<float *>(smem_raw);             // [RED_SL][RC] slice sums
     double *sq = reinterpret_cast<double *>(smem_raw + 8192);         // [RC] squared gradients
-    double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slice
+    double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slices
     const bool sharded = opt.world > 1;
-    // destination of the locally reduced gradient: the final gradient buffer, or (sharded) my peer-visible exchange buffer
-    float *gdst = sharded ? opt.peers[opt.rank] + (int)(opt_step & 1) * opt.gstride : opt.grad;
     // losses of the whole launch (one warp of CTA 0; the other CTAs' loss partials were written before the first grid barrier)
     if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
-    for (int c0 = 0; c0 < n_i; c0 += RC) {
-        const int nc = min(RC, n_i - c0);
+    // sharded: exchange buffer of rank r = {inbox[2 (step parity)][world (sender)][gstride] float, flags[world (sender)][nsl] u32}
+    const unsigned int epoch = (unsigned int)opt_step;
+    const int inbox_off = (int)(opt_step & 1) * opt.world * opt.gstride;   // this step's inbox, in floats
+    const int flag_off = 2 * opt.world * opt.gstride;                      // in 4-byte words
+    __shared__ int peers_ok;
+    if (tid == 0) peers_ok = 1;   // (made visible by the barriers inside the loop before anybody reads it)
+    for (int sidx = blockIdx.x; sidx < nsl; sidx += nb) {
+        const int p0 = sidx * RC, nc = min(RC, P - p0);
         for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
             const int sl = item / nc, pi = item - sl * nc;
-            sl_part[sl * RC + pi] = reduce_slice(partials, nb, part_stride, i0 + c0 + pi, sl);
+            sl_part[sl * RC + pi] = reduce_slice(partials, nb, part_stride, p0 + pi, sl);
         }
         __syncthreads();
+        float gi = 0.f;
         if (tid < nc) {
             float t16[RED_SL];
 #pragma unroll
             for (int u = 0; u < RED_SL; ++u) t16[u] = sl_part[u * RC + tid];
-            const float gi = reduce_tree(t16);
-            gdst[i0 + c0 + tid] = gi;
+            gi = reduce_tree(t16);
+        }
+        if (sharded) {
+            // ---- gradient exchange over peer memory, slice by slice, with no further grid-wide step: PUSH my reduced slice
+            // into every rank's inbox (slot = my rank), raise the slice's flag there, wait for the same slice from every
+            // rank in my own inbox, sum in rank order (identical result on every rank) - the allreduce, inside the kernel
+            if (tid < nc)
+                for (int pr = 0; pr < opt.world; ++pr) opt.peers[pr][inbox_off + opt.rank * opt.gstride + p0 + tid] = gi;
+            __syncthreads();
+            if (tid < opt.world) {
+                __threadfence_system();
+                st_release_sys(reinterpret_cast<unsigned int *>(opt.peers[tid]) + flag_off + opt.rank * nsl + sidx, epoch);
+                // ... and wait for rank tid's copy of this slice
+                const unsigned int *f = reinterpret_cast<const unsigned int *>(opt.peers[opt.rank]) + flag_off + tid * nsl + sidx;
+                int ok = 0;
+                for (int itp = 0; itp < (1 << 24); ++itp)
+                    if ((int)(ld_acquire_sys(f) - epoch) >= 0) { ok = 1; break; }
+                if (!ok) peers_ok = 0;
+            }
+            __syncthreads();
+            if (!peers_ok) { if (tid == 0) atomicExch(status, 3); return; }
+            if (tid < nc) {
+                const float *in = opt.peers[opt.rank] + inbox_off + p0 + tid;
+                float g = 0.f;
+                for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 loads in flight, summed in rank order
+                    float pv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pv[u] = r0 + u < opt.world ? ld_relaxed_sys(in + (r0 + u) * opt.gstride) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (r0 + u < opt.world) g += pv[u];
+                }
+                gi = g;
+            }
+        }
+        if (tid < nc) {
+            opt.grad[p0 + tid] = gi;
             sq[tid] = (double)gi * gi;
         }
         __syncthreads();
         if (tid == 0)
             for (int k = 0; k < nc; ++k) ssum += sq[k];
-    }
-    if (sharded) {
-        // ---- gradient exchange over peer memory: my reduced slice sits in my exchange buffer; once every CTA has written
-        // its slice, CTA 0 raises my flag on every rank; then each CTA sums the W ranks' buffers over its slice in rank
-        // order (identical result on every rank) - the allreduce, without leaving the kernel
-        if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
-        const unsigned int epoch = (unsigned int)opt_step;
-        const int flag_off = 2 * opt.gstride;   // in 4-byte words
-        if (blockIdx.x == 0 && tid < opt.world) {
-            __threadfence_system();
-            st_release_sys(reinterpret_cast<unsigned int *>(opt.peers[tid]) + flag_off + opt.rank, epoch);
-        }
-        __shared__ int peers_ok;
-        if (tid == 0) {
-            const unsigned int *myflags = reinterpret_cast<const unsigned int *>(opt.peers[opt.rank]) + flag_off;
-            int ok = 1;
-            for (int rr = 0; rr < opt.world && ok; ++rr) {
-                ok = 0;
-                for (int itp = 0; itp < (1 << 24); ++itp)
-                    if ((int)(ld_acquire_sys(myflags + rr) - epoch) >= 0) { ok = 1; break; }
-            }
-            peers_ok = ok;
-        }
         __syncthreads();
-        if (!peers_ok) { if (tid == 0) atomicExch(status, 3); return; }
-        ssum = 0.0;
-        const int goff = (int)(opt_step & 1) * opt.gstride;
-        for (int c0 = 0; c0 < n_i; c0 += RC) {
-            const int nc = min(RC, n_i - c0);
-            if (tid < nc) {
-                float g = 0.f;
-                for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 peer loads in flight, summed in rank order
-                    float pv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) pv[u] = r0 + u < opt.world ? ld_relaxed_sys(opt.peers[r0 + u] + goff + i0 + c0 + tid) : 0.f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (r0 + u < opt.world) g += pv[u];
-                }
-                opt.grad[i0 + c0 + tid] = g;
-                sq[tid] = (double)g * g;
-            }
-            __syncthreads();
-            if (tid == 0)
-                for (int k = 0; k < nc; ++k) ssum += sq[k];
-            __syncthreads();
-        }
     }
     if (tid == 0) opt.sumsq[blockIdx.x] = ssum;
     TC_SPAN0(1);
@@ -914,8 +910,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
         const float step_size = (float)((double)opt.lr / (1.0 - opt_p1)), bc2_sqrt = (float)sqrt(1.0 - opt_p2);
         const float coef = coef_s, decay = 1.0f - opt.lr * opt.wd;
-        for (int k = tid; k < n_i; k += TC_THREADS) {
-            const int i = i0 + k;
+        for (int k = tid; k < RC * ((nsl - (int)blockIdx.x + nb - 1) / nb); k += TC_THREADS) {
+            const int i = ((int)blockIdx.x + (k / RC) * nb) * RC + (k % RC);   // slice blockIdx.x + j nb, element k % RC
+            if (i >= P) continue;
             const float g = opt.grad[i] * coef;      // written by this CTA above
             float pv = opt.params_rw[i] * decay;
             const float mi = opt.m[i] + (1.0f - b1) * (g - opt.m[i]);
@@ -1098,7 +1095,8 @@ int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int actio
 
 size_t prl_p2p_exchange_bytes(int is_continuous, int obs_dim, int action_dim, int world) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    return ((size_t)2 * ((L.total + 3) & ~3) + (size_t)world) * 4 + 256;
+    const size_t gstride = (L.total + 3) & ~3, nsl = (L.total + 63) / 64;   // inbox[2][world][gstride] floats + flags[world][nsl]
+    return ((size_t)2 * world * gstride + (size_t)world * nsl) * 4 + 256;
 }
 int prl_p2p_alloc(size_t bytes, void **ptr) {
     PRL_REQUIRE(ptr && bytes > 0, "prl_p2p_alloc: bad arguments");
