@@ -218,7 +218,7 @@ struct TcOptimizer {
     double *loss_out;                         // 4 doubles, accumulated
     double rows;
     // sharded runs: the gradient exchange happens inside this kernel over NVLink peer memory instead of an NCCL allreduce.
-    // peers[r] = base of rank r's exchange buffer {inbox[2 (step parity)][world (sender)][gstride] float, flags[world][slices] u32}
+    // peers[r] = base of rank r's exchange buffer: inbox[2 (step parity)][world (sender)][gstride] words {float bits, step number}
     float *const *peers;
     int rank, world, gstride;
 };
@@ -230,6 +230,14 @@ __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float ld_relaxed_sys(const float *p) {
@@ -821,10 +829,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const bool sharded = opt.world > 1;
     // losses of the whole launch (one warp of CTA 0; the other CTAs' loss partials were written before the first grid barrier)
     if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
-    // sharded: exchange buffer of rank r = {inbox[2 (step parity)][world (sender)][gstride] float, flags[world (sender)][nsl] u32}
+    // sharded: exchange buffer of rank r = inbox[2 (step parity)][world (sender)][gstride] 8-byte words {float bits, step number}
     const unsigned int epoch = (unsigned int)opt_step;
-    const int inbox_off = (int)(opt_step & 1) * opt.world * opt.gstride;   // this step's inbox, in floats
-    const int flag_off = 2 * opt.world * opt.gstride;                      // in 4-byte words
+    const int inbox_off = (int)(opt_step & 1) * opt.world * opt.gstride;   // this step's inbox, in words
     __shared__ int peers_ok;
     if (tid == 0) peers_ok = 1;   // (made visible by the barriers inside the loop before anybody reads it)
     for (int sidx = blockIdx.x; sidx < nsl; sidx += nb) {
@@ -842,37 +849,39 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             gi = reduce_tree(t16);
         }
         if (sharded) {
-            // ---- gradient exchange over peer memory, slice by slice, with no further grid-wide step: PUSH my reduced slice
-            // into every rank's inbox (slot = my rank), raise the slice's flag there, wait for the same slice from every
-            // rank in my own inbox, sum in rank order (identical result on every rank) - the allreduce, inside the kernel
-            if (tid < nc)
-                for (int pr = 0; pr < opt.world; ++pr) opt.peers[pr][inbox_off + opt.rank * opt.gstride + p0 + tid] = gi;
-            __syncthreads();
-            if (tid < opt.world) {
-                __threadfence_system();
-                st_release_sys(reinterpret_cast<unsigned int *>(opt.peers[tid]) + flag_off + opt.rank * nsl + sidx, epoch);
-                // ... and wait for rank tid's copy of this slice
-                const unsigned int *f = reinterpret_cast<const unsigned int *>(opt.peers[opt.rank]) + flag_off + tid * nsl + sidx;
-                int ok = 0;
-                for (int itp = 0; itp < (1 << 24); ++itp)
-                    if ((int)(ld_acquire_sys(f) - epoch) >= 0) { ok = 1; break; }
+            // ---- gradient exchange over peer memory, slice by slice, with no further grid-wide step and no separate flag:
+            // every value travels as one 8-byte word {float bits, step number} (a naturally aligned 64-bit store is single-copy
+            // atomic), PUSHED into every rank's inbox (slot = my rank); the receiver polls the words of its own inbox until
+            // they carry this step's number and sums them in rank order (identical result on every rank) - the allreduce,
+            // inside the kernel, one NVLink one-way latency long
+            if (tid < nc) {
+                const unsigned long long word = ((unsigned long long)epoch << 32) | __float_as_uint(gi);
+                for (int pr = 0; pr < opt.world; ++pr)
+                    st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(opt.peers[pr]) + inbox_off + opt.rank * opt.gstride + p0 + tid, word);
+                const unsigned long long *in = reinterpret_cast<const unsigned long long *>(opt.peers[opt.rank]) + inbox_off + p0 + tid;
+                float g = 0.f;
+                bool ok = true;
+                for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 ranks polled together, summed in rank order
+                    unsigned long long pv[8];
+                    bool all = false;
+                    for (int itp = 0; itp < (1 << 22) && !all; ++itp) {
+                        all = true;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            pv[u] = r0 + u < opt.world ? ld_relaxed_sys_u64(in + (r0 + u) * opt.gstride) : ((unsigned long long)epoch << 32);
+                            all = all && (unsigned int)(pv[u] >> 32) == epoch;
+                        }
+                    }
+                    ok = ok && all;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (r0 + u < opt.world) g += __uint_as_float((unsigned int)pv[u]);
+                }
                 if (!ok) peers_ok = 0;
+                gi = g;
             }
             __syncthreads();
             if (!peers_ok) { if (tid == 0) atomicExch(status, 3); return; }
-            if (tid < nc) {
-                const float *in = opt.peers[opt.rank] + inbox_off + p0 + tid;
-                float g = 0.f;
-                for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 loads in flight, summed in rank order
-                    float pv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) pv[u] = r0 + u < opt.world ? ld_relaxed_sys(in + (r0 + u) * opt.gstride) : 0.f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (r0 + u < opt.world) g += pv[u];
-                }
-                gi = g;
-            }
         }
         if (tid < nc) {
             opt.grad[p0 + tid] = gi;
@@ -1095,8 +1104,8 @@ int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int actio
 
 size_t prl_p2p_exchange_bytes(int is_continuous, int obs_dim, int action_dim, int world) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    const size_t gstride = (L.total + 3) & ~3, nsl = (L.total + 63) / 64;   // inbox[2][world][gstride] floats + flags[world][nsl]
-    return ((size_t)2 * world * gstride + (size_t)world * nsl) * 4 + 256;
+    const size_t gstride = (L.total + 3) & ~3;   // inbox[2][world][gstride] 8-byte words
+    return (size_t)2 * world * gstride * 8 + 256;
 }
 int prl_p2p_alloc(size_t bytes, void **ptr) {
     PRL_REQUIRE(ptr && bytes > 0, "prl_p2p_alloc: bad arguments");
