@@ -212,7 +212,8 @@ struct TcOptimizer {
     float *params_rw, *grad, *m, *v;          // params_rw == nullptr: gradient only (the reduction runs as a separate kernel)
     int64_t *clock;                           // {int64 step, double beta1^step, double beta2^step}
     unsigned int *sync;                       // {arrival count, generation} of the grid barrier
-    double *sumsq;                            // [grid] squared-norm partials
+    double *sumsq;                            // [grid] squared-norm partials (unused by the fused step: tagged words instead)
+    unsigned long long *tagw;                 // [grid][8] tagged words: loss sums (3 doubles = 6 words), squared norm (2 words)
     double *norm_out;
     float lr, wd, max_norm;
     double *loss_out;                         // 4 doubles, accumulated
@@ -239,6 +240,33 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// tagged words inside one GPU: {32 payload bits, step number}; a naturally aligned 64-bit access is single-copy atomic, so a
+// reader that sees this launch's step number also sees the payload - no fence, no barrier between producer and consumer
+__device__ __forceinline__ void st_tag(unsigned long long *p, unsigned int payload, unsigned int epoch) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | payload;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_tag(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_tag_double(unsigned long long *p2, double x, unsigned int epoch) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    st_tag(p2, (unsigned int)(b >> 32), epoch);
+    st_tag(p2 + 1, (unsigned int)b, epoch);
+}
+// polls until both halves carry `epoch` (bounded); ok is cleared on a time-out
+__device__ __forceinline__ double ld_tag_double(const unsigned long long *p2, unsigned int epoch, bool &ok) {
+    unsigned long long hi = 0, lo = 0;
+    bool got = false;
+    for (int it = 0; it < (1 << 22) && !got; ++it) {
+        hi = ld_tag(p2); lo = ld_tag(p2 + 1);
+        got = (unsigned int)(hi >> 32) == epoch && (unsigned int)(lo >> 32) == epoch;
+    }
+    ok = ok && got;
+    return __longlong_as_double((long long)(((hi & 0xffffffffull) << 32) | (lo & 0xffffffffull)));
 }
 __device__ __forceinline__ float ld_relaxed_sys(const float *p) {
     float v;
@@ -287,6 +315,29 @@ __device__ __forceinline__ float reduce_slice(const float *__restrict__ partials
         }
 #pragma unroll
         for (int u = 0; u < RED_MAX; ++u) s += v[u];
+    }
+    return s;
+}
+// the same over TAGGED partial rows (fused step): every word is polled until it carries this launch's step number, so the
+// reduction needs no grid barrier behind the producers; the summation order is the one above (bit-identical result)
+__device__ __forceinline__ float reduce_slice_tagged(const unsigned long long *__restrict__ partials, int nblocks, int stride, int i, int sl,
+                                                     unsigned int epoch, bool &ok) {
+    float s = 0.f;
+    for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
+        unsigned long long v[RED_MAX];
+        bool all = false;
+        for (int it = 0; it < (1 << 22) && !all; ++it) {
+            all = true;
+#pragma unroll
+            for (int u = 0; u < RED_MAX; ++u) {
+                const int bl = base + u * RED_SL;
+                v[u] = bl < nblocks ? ld_tag(partials + (size_t)bl * stride + i) : ((unsigned long long)epoch << 32);
+                all = all && (unsigned int)(v[u] >> 32) == epoch;
+            }
+        }
+        ok = ok && all;
+#pragma unroll
+        for (int u = 0; u < RED_MAX; ++u) s += __uint_as_float((unsigned int)v[u]);
     }
     return s;
 }
@@ -431,6 +482,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
     const int P = L.total;
     float *part = partials + (size_t)blockIdx.x * part_stride;
+    // fused optimiser step: this CTA's partial row is written as tagged 64-bit words (see st_tag)
+    const bool fused = opt.params_rw != nullptr;
+    unsigned long long *part64 = reinterpret_cast<unsigned long long *>(partials) + (size_t)blockIdx.x * part_stride;
     // optimiser clock, read before anybody can advance it (CTA 0 does, after the second grid barrier)
     int64_t opt_step = 0;
     double opt_p1 = 0.0, opt_p2 = 0.0;
@@ -441,6 +495,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         opt_p1 = have ? pw[0] * 0.9 : pow(0.9, (double)opt_step);
         opt_p2 = have ? pw[1] * 0.999 : pow(0.999, (double)opt_step);
     }
+    // the tag of every word this launch publishes inside the GPU: a launch counter kept in the workspace header (word 3),
+    // read by everybody here and advanced by CTA 0 at the very end - monotonic per workspace, whatever optimiser uses it
+    const unsigned int epoch = fused ? __ldcg(reinterpret_cast<const unsigned int *>(status) + 3) + 1u : 0u;
+    // one partial-gradient entry: plain float (separate reduction kernel) or tagged word (fused step)
+    auto put = [&](int idx, float v) {
+        if (fused) st_tag(part64 + idx, __float_as_uint(v), epoch);
+        else part[idx] = v;
+    };
 
     if (is_mma_warp) {
         // =============================================================================== MMA-issue warp
@@ -762,15 +824,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 for (int i = 0; i < TC_W; ++i) scratch2[r * 17 + i] = v2[i];
             }
             bar_compute();
-            float *dst0 = part + L.head[0].w1, *dst1 = part + L.head[1].w1;
             for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
                 const int j = idx >> 6, k = idx & 63;
-                dst0[idx] = (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f;
-                dst1[idx] = (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f;
+                put(L.head[0].w1 + idx, (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f);
+                put(L.head[1].w1 + idx, (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f);
             }
             for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
                 const int j = idx / O, i = idx - j * O;
-                part[L.w0 + idx] = (it > 0) ? scratch2[j * 17 + i] + scratch2[(64 + j) * 17 + i] : 0.f;
+                put(L.w0 + idx, (it > 0) ? scratch2[j * 17 + i] + scratch2[(64 + j) * 17 + i] : 0.f);
             }
         }
         // column-sum accumulators (already in s_red / b2s): combine the four row quarters
@@ -787,11 +848,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     if (k >= 2 + L.head[0].out) { k -= 2 + L.head[0].out; h = 1; }
                     off = (k == 0) ? L.head[h].gw : (k == 1) ? L.head[h].gb : L.head[h].w2 + (k - 2) * HID;
                 }
-                part[off + j] = sm;
+                put(off + j, sm);
             }
             if (tid < 2 * NA) {
                 const int h = tid / NA, a = tid % NA;
-                if (a < L.head[h].out) part[L.head[h].b2 + a] = (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]);
+                if (a < L.head[h].out) put(L.head[h].b2 + a, (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]));
             }
         }
         TC_STAMP(15);
@@ -801,10 +862,16 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const double bv = block_sum<double>(l_val, red);
     const double be = block_sum<double>(l_ent, red);
     if (tid == 0) {
-        loss_partials[blockIdx.x * 4 + 0] = bp;
-        loss_partials[blockIdx.x * 4 + 1] = bv;
-        loss_partials[blockIdx.x * 4 + 2] = be;
-        loss_partials[blockIdx.x * 4 + 3] = 0.0;
+        if (fused) {
+            st_tag_double(opt.tagw + blockIdx.x * 8 + 0, bp, epoch);
+            st_tag_double(opt.tagw + blockIdx.x * 8 + 2, bv, epoch);
+            st_tag_double(opt.tagw + blockIdx.x * 8 + 4, be, epoch);
+        } else {
+            loss_partials[blockIdx.x * 4 + 0] = bp;
+            loss_partials[blockIdx.x * 4 + 1] = bv;
+            loss_partials[blockIdx.x * 4 + 2] = be;
+            loss_partials[blockIdx.x * 4 + 3] = 0.0;
+        }
     }
     if (!mma_ok && lane == 0) atomicExch(status, 1);
     fence_before_sync();
@@ -815,9 +882,12 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     TC_SPAN(3);
     if (!opt.params_rw) return;
 
-    // ================= fused optimiser tail: reduce -> clip_grad_norm_ -> AdamW on this CTA's slice of the parameters
+    // ================= fused optimiser tail: reduce -> clip_grad_norm_ -> AdamW on this CTA's slices of the parameters.
+    // No grid barrier anywhere: every CTA published its partial row, loss sums and (below) squared norm as TAGGED words, and
+    // the consumers poll the words they need until they carry this launch's step number.  (All CTAs are co-resident -
+    // cooperative launch - so the polls terminate; they are bounded anyway: status 2.)
     const int nb = gridDim.x;
-    if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
+    bool tags_ok = true;
     TC_SPAN0(0);
     // The parameters are cut into slices of RC = 64 (142 slices for P = 9 027); CTA c owns slices c, c + nb, ...  The cut does
     // not depend on the grid, so ranks whose minibatches have different row counts (different grids) agree on it.
@@ -828,9 +898,22 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slices
     const bool sharded = opt.world > 1;
     // losses of the whole launch (one warp of CTA 0; the other CTAs' loss partials were written before the first grid barrier)
-    if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
+    if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) {
+        // lane l adds blocks l, l + 32, ... in ascending order, then a fixed shuffle tree: bit-reproducible
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int bl = lane; bl < nb; bl += 32) {
+            a0 += ld_tag_double(opt.tagw + bl * 8 + 0, epoch, tags_ok);
+            a1 += ld_tag_double(opt.tagw + bl * 8 + 2, epoch, tags_ok);
+            a2 += ld_tag_double(opt.tagw + bl * 8 + 4, epoch, tags_ok);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
+    }
     // sharded: exchange buffer of rank r = inbox[2 (step parity)][world (sender)][gstride] 8-byte words {float bits, step number}
-    const unsigned int epoch = (unsigned int)opt_step;
+    const unsigned int xepoch = (unsigned int)opt_step;   // the ranks agree on the optimiser step, not on launch counters
     const int inbox_off = (int)(opt_step & 1) * opt.world * opt.gstride;   // this step's inbox, in words
     __shared__ int peers_ok;
     if (tid == 0) peers_ok = 1;   // (made visible by the barriers inside the loop before anybody reads it)
@@ -838,7 +921,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         const int p0 = sidx * RC, nc = min(RC, P - p0);
         for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
             const int sl = item / nc, pi = item - sl * nc;
-            sl_part[sl * RC + pi] = reduce_slice(partials, nb, part_stride, p0 + pi, sl);
+            sl_part[sl * RC + pi] = reduce_slice_tagged(reinterpret_cast<const unsigned long long *>(partials), nb, part_stride, p0 + pi, sl, epoch, tags_ok);
         }
         __syncthreads();
         float gi = 0.f;
@@ -855,7 +938,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             // they carry this step's number and sums them in rank order (identical result on every rank) - the allreduce,
             // inside the kernel, one NVLink one-way latency long
             if (tid < nc) {
-                const unsigned long long word = ((unsigned long long)epoch << 32) | __float_as_uint(gi);
+                const unsigned long long word = ((unsigned long long)xepoch << 32) | __float_as_uint(gi);
                 for (int pr = 0; pr < opt.world; ++pr)
                     st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(opt.peers[pr]) + inbox_off + opt.rank * opt.gstride + p0 + tid, word);
                 const unsigned long long *in = reinterpret_cast<const unsigned long long *>(opt.peers[opt.rank]) + inbox_off + p0 + tid;
@@ -868,8 +951,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                         all = true;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            pv[u] = r0 + u < opt.world ? ld_relaxed_sys_u64(in + (r0 + u) * opt.gstride) : ((unsigned long long)epoch << 32);
-                            all = all && (unsigned int)(pv[u] >> 32) == epoch;
+                            pv[u] = r0 + u < opt.world ? ld_relaxed_sys_u64(in + (r0 + u) * opt.gstride) : ((unsigned long long)xepoch << 32);
+                            all = all && (unsigned int)(pv[u] >> 32) == xepoch;
                         }
                     }
                     ok = ok && all;
@@ -892,15 +975,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int k = 0; k < nc; ++k) ssum += sq[k];
         __syncthreads();
     }
-    if (tid == 0) opt.sumsq[blockIdx.x] = ssum;
+    if (tid == 0) st_tag_double(opt.tagw + blockIdx.x * 8 + 6, ssum, epoch);
     TC_SPAN0(1);
-    if (!grid_barrier(opt.sync, nb)) { if (tid == 0) atomicExch(status, 2); return; }
     TC_SPAN0(2);
     __shared__ float coef_s;
     if (warp == 0) {
-        // total squared norm in a fixed order: lane l adds partials l, l + 32, ...; then a fixed shuffle tree
+        // total squared norm in a fixed order: lane l adds the CTAs' (tagged) partials l, l + 32, ...; then a fixed shuffle tree
         double a = 0.0;
-        for (int k = lane; k < nb; k += 32) a += __ldcg(opt.sumsq + k);
+        for (int k = lane; k < nb; k += 32) a += ld_tag_double(opt.tagw + k * 8 + 6, epoch, tags_ok);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) {
@@ -910,9 +992,11 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 if (opt.norm_out) *opt.norm_out = (double)total;
                 double *pw = reinterpret_cast<double *>(opt.clock) + 1;
                 opt.clock[0] = opt_step; pw[0] = opt_p1; pw[1] = opt_p2;
+                reinterpret_cast<unsigned int *>(status)[3] = epoch;   // the launch counter (every CTA read it at its start)
             }
         }
     }
+    if (!tags_ok) atomicExch(status, 2);
     __syncthreads();
     TC_SPAN0(3);
     {
@@ -978,8 +1062,10 @@ static int tc_grid_max(int64_t b) {
     const int64_t nt = (b + TC_ROWS - 1) / TC_ROWS;
     return (int)(nt < sms ? (nt > 0 ? nt : 1) : sms);
 }
+// header (4 words: status, 2 barrier words, launch counter) | partial rows (8-byte tagged words in the fused step, floats
+// otherwise) | loss partials (4 doubles per CTA) | squared-norm partials (1 double) | tagged scalars (8 words per CTA)
 static size_t tc_ws_floats(const PolicyLayout &L, int grid) {
-    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + 16;
+    return 4 + (size_t)2 * grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + (size_t)grid * 16 + 16;
 }
 
 }  // namespace prl
@@ -1019,12 +1105,13 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
     // re-zeroed before every fused launch), then per-CTA partial gradients, loss partials, squared-norm partials
     int *status = reinterpret_cast<int *>(ws);
     float *partials = ws + 4;
-    double *loss_partials = reinterpret_cast<double *>(partials + (size_t)grid * pstride);
+    double *loss_partials = reinterpret_cast<double *>(partials + (size_t)2 * grid * pstride);
     TcOptimizer opt{};
     if (optp) {
         opt = *optp;
         opt.sync = reinterpret_cast<unsigned int *>(ws) + 1;
         opt.sumsq = loss_partials + (size_t)grid * 4;
+        opt.tagw = reinterpret_cast<unsigned long long *>(opt.sumsq + grid);
     }
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
