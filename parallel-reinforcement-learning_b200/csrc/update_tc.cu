@@ -303,7 +303,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nbl
 }
 
 // sum over the CTAs' partial rows of parameter i, slice sl of RED_SL (blocks sl, sl + RED_SL, ... in ascending order)
-constexpr int RED_SL = 16, RED_MAX = 10;   // (8 x 19 would be one L2 round trip, but 19 live loads per thread spill: measured)
+constexpr int RED_SL = 8, RED_MAX = 19;   // 8 x 19 >= 148 CTAs: every word of a slice is in flight at once (one L2 round trip, one pass of the threads)
 __device__ __forceinline__ float reduce_slice(const float *__restrict__ partials, int nblocks, int stride, int i, int sl) {
     float s = 0.f;
     for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
@@ -327,6 +327,7 @@ __device__ __forceinline__ float reduce_slice_tagged(const unsigned long long *_
         unsigned long long v[RED_MAX];
         bool all = false;
         for (int it = 0; it < (1 << 22) && !all; ++it) {
+            if (it) __nanosleep(400);   // the poll of a whole grid is ~11 MB of L2 reads per round: leave the producers their bandwidth
             all = true;
 #pragma unroll
             for (int u = 0; u < RED_MAX; ++u) {
