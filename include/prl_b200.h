@@ -45,6 +45,8 @@ size_t prl_scan_ws_bytes(int64_t n);
 /* ---------------------------------------------------------------- test hooks (parity tests only) */
 int prl_test_sincos(const double *x, double *sin_out, double *cos_out, int64_t n, void *stream);
 int prl_test_pow2(const double *x, double *out, const float *xf, float *outf, int64_t n, void *stream);
+/* out[i][k] = k-th 64-bit output of np.random.PCG64(np.random.SeedSequence(seeds[i])) */
+int prl_test_pcg64(const uint64_t *seeds, int n, int draws, uint64_t *out, void *stream);
 int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
 /* tensor-core building blocks (csrc/umma.cuh): one 128-row tile, tcgen05.mma kind::tf32 from shared memory.
  * mode 0: D[128][128] = A[128][64] B[128][64]^T; 1: D[128][64] = A[128][64] B[64:128][0:64]; 2: D[128][64] =
@@ -57,6 +59,12 @@ int prl_test_umma(int mode, const float *A, const float *B, float *D, int *statu
  * zeroes the TimeLimit counters and the terminal mask, writes obs [E][O] float32. */
 int prl_env_reset(int env_id, int E, uint64_t seed, uint64_t episode, double *state, int32_t *elapsed,
                   uint8_t *terminal, float *obs, void *stream);
+/* reset() from numpy's seeded stream - what E gymnasium envs seeded with env.reset(seed=seeds[e]) draw (the per-env
+ * call at AsyncPPO.py:53): rng is [4][E] uint64 {state_hi, state_lo, inc_hi, inc_lo} of one PCG64 per env.  seeds != NULL:
+ * generator e is first created as np.random.PCG64(np.random.SeedSequence(seeds[e])); seeds == NULL: the stored
+ * generators continue (a later reset() of the same envs).  States = Generator.uniform(low, high), bit for bit. */
+int prl_env_reset_numpy(int env_id, int E, const uint64_t *seeds, uint64_t *rng, double *state, int32_t *elapsed,
+                        uint8_t *terminal, float *obs, void *stream);
 /* reset() with injected start states (teacher forcing): state_aos is [E][S] fp64. */
 int prl_env_set_state(int env_id, int E, const double *state_aos, double *state, int32_t *elapsed,
                       uint8_t *terminal, float *obs, void *stream);

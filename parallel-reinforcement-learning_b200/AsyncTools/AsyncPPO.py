@@ -171,14 +171,25 @@ class EnvVectorizer:
         v = np.ascontiguousarray(np.asarray(value, dtype=np.bool_).reshape(self.num_envs))
         self.sim.terminal.copy_(t.from_numpy(v.view(np.uint8)))
 
-    def reset_device(self) -> t.Tensor:
+    def reset_device(self, seed=None) -> t.Tensor:
         self.episode += 1
         self.t = 0
+        if seed is not None:
+            # numpy-identical seeded resets: env i becomes what `envs[i].reset(seed=seeds[i])` gives in the reference
+            # (gymnasium: Generator(PCG64(SeedSequence(seed))).uniform(low, high)); an int seeds env i with seed + i
+            seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(seed) if np.isscalar(seed) else np.asarray(seed, dtype=np.uint64)
+            if seeds.shape != (self.num_envs,):
+                raise ValueError(f"seed must be an int or {self.num_envs} ints")
+            self._numpy_stream = True
+            return self.sim.reset_numpy(t.from_numpy(seeds.view(np.int64)).to(self.device))
+        if getattr(self, "_numpy_stream", False):
+            return self.sim.reset_numpy()   # every env's generator continues, as the reference's per-env generators do
         return self.sim.reset(self.seed, self.episode)
 
-    def reset(self):
-        """AsyncPPO.py:48-62 -> (obs [E, O] float32, infos)."""
-        obs = self.reset_device()
+    def reset(self, seed=None):
+        """AsyncPPO.py:48-62 -> (obs [E, O] float32, infos).  `seed` (an extension; the reference's reset() cannot be
+        seeded): int or num_envs ints - see reset_device."""
+        obs = self.reset_device(seed)
         return obs.cpu().numpy(), [{} for _ in range(self.num_envs)]
 
     def reset_to_device(self, states) -> t.Tensor:

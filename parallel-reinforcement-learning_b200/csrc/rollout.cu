@@ -3,6 +3,7 @@
 //
 // Reference: /root/reference/AsyncTools/AsyncPPO.py:11-146, AsyncTools/utils.py:1-50, PPO/PPO.py:82-96.
 #include "envs.cuh"
+#include "np_rng.cuh"
 #include "policy.cuh"
 #include "tiled_mlp.cuh"
 
@@ -57,6 +58,43 @@ __global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__re
     float o[ENV::O];
     ENV::obs(s, o);
     store_obs_row<ENV>(obs, e, o);
+}
+
+// reset() from numpy's seeded stream (np_rng.cuh): env e owns a PCG64 generator in rng[4][E]; with `seeds` it is first
+// (re)created as PCG64(SeedSequence(seeds[e])) - gymnasium's env.reset(seed=...) - then RESET_DRAWS doubles are drawn
+// as Generator.uniform(low, high) does and the advanced generator is stored back, so later resets continue the stream.
+template <class ENV>
+__global__ void k_env_reset_numpy(int E, const uint64_t *__restrict__ seeds, uint64_t *__restrict__ rng, double *__restrict__ state,
+                                  int32_t *__restrict__ elapsed, uint8_t *__restrict__ terminal, float *__restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Pcg64 g;
+    if (seeds) g = Pcg64::from_seed(seeds[e]);
+    else { g.shi = rng[e]; g.slo = rng[(size_t)E + e]; g.ihi = rng[2 * (size_t)E + e]; g.ilo = rng[3 * (size_t)E + e]; }
+    double s[ENV::S];
+#pragma unroll
+    for (int i = 0; i < ENV::S; ++i) {
+        if (i >= ENV::RESET_DRAWS) { s[i] = 0.0; continue; }
+        const double hi = ENV::reset_hi(i), lo = ENV::reset_lo(i);
+        double v = dadd(lo, dmul(dsub(hi, lo), g.next_double()));   // random_uniform: low + range * next_double
+        if (ENV::RESET_F32) v = (double)(float)v;
+        s[i] = v;
+    }
+    rng[e] = g.shi; rng[(size_t)E + e] = g.slo; rng[2 * (size_t)E + e] = g.ihi; rng[3 * (size_t)E + e] = g.ilo;
+    store_state<ENV>(state, E, e, s);
+    elapsed[e] = 0;
+    terminal[e] = 0;
+    float o[ENV::O];
+    ENV::obs(s, o);
+    store_obs_row<ENV>(obs, e, o);
+}
+
+// test hook: out[i][k] = k-th 64-bit output of PCG64(SeedSequence(seeds[i]))
+__global__ void k_test_pcg64(const uint64_t *__restrict__ seeds, int n, int draws, uint64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pcg64 g = Pcg64::from_seed(seeds[i]);
+    for (int k = 0; k < draws; ++k) out[(size_t)i * draws + k] = g.next64();
 }
 
 template <class ENV>
@@ -500,6 +538,22 @@ int prl_env_reset(int env_id, int E, uint64_t seed, uint64_t episode, double *st
         k_env_reset<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, seed, episode, state, elapsed, terminal, obs);
         return check_launch("k_env_reset");
     });
+}
+
+int prl_env_reset_numpy(int env_id, int E, const uint64_t *seeds, uint64_t *rng, double *state, int32_t *elapsed,
+                        uint8_t *terminal, float *obs, void *stream) {
+    PRL_REQUIRE(E > 0 && rng && state && elapsed && terminal && obs, "prl_env_reset_numpy: bad arguments (E=%d)", E);
+    return dispatch_env(env_id, [&](auto env) -> int {
+        using ENV = decltype(env);
+        k_env_reset_numpy<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, seeds, rng, state, elapsed, terminal, obs);
+        return check_launch("k_env_reset_numpy");
+    });
+}
+
+int prl_test_pcg64(const uint64_t *seeds, int n, int draws, uint64_t *out, void *stream) {
+    PRL_REQUIRE(seeds && out && n > 0 && draws > 0, "prl_test_pcg64: bad arguments");
+    k_test_pcg64<<<cdiv(n, TPB), TPB, 0, (cudaStream_t)stream>>>(seeds, n, draws, out);
+    return check_launch("k_test_pcg64");
 }
 
 int prl_env_set_state(int env_id, int E, const double *state_aos, double *state, int32_t *elapsed, uint8_t *terminal,

@@ -30,6 +30,8 @@ PROTOTYPES = {
     "prl_test_philox": (_i32, [_u64, _u32, _u32, _u32, _u32, _vp, _vp]),
     "prl_test_umma": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "prl_env_reset": (_i32, [_i32, _i32, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "prl_env_reset_numpy": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_test_pcg64": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "prl_env_set_state": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "prl_env_get_state": (_i32, [_i32, _i32, _vp, _vp, _vp]),
     "prl_env_step": (_i32, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -103,7 +105,7 @@ def require_cuda():
 
 # kernels launched by one call of each entry point (csrc/*.cu) - used to count launches, e.g. by bench.py
 KERNELS_PER_CALL = {
-    "prl_test_sincos": 1, "prl_test_pow2": 1, "prl_test_philox": 1, "prl_test_umma": 1, "prl_env_reset": 1, "prl_env_set_state": 1,
+    "prl_test_sincos": 1, "prl_test_pow2": 1, "prl_test_philox": 1, "prl_test_umma": 1, "prl_env_reset": 1, "prl_env_reset_numpy": 1, "prl_test_pcg64": 1, "prl_env_set_state": 1,
     "prl_env_get_state": 1, "prl_env_step": 1, "prl_compact_indices": 2, "prl_gather_rows": 1, "prl_mask_update": 1,
     "prl_buffer_append": 1, "prl_buffer_transfer": 4, "prl_policy_act": 1, "prl_policy_evaluate": 1, "prl_rollout": 1,
     "prl_gae": 1, "prl_gae_columns": 1, "prl_adv_normalize": 1, "prl_ppo_grad": 2, "prl_ppo_grad_tc": 2, "prl_ppo_step_tc": 1, "prl_ppo_step_tc_p2p": 1, "prl_adamw_step": 1, "prl_adamw_step_dev": 1,

@@ -62,6 +62,15 @@ def test_philox(seed, c0, c1, c2, c3):
     return out.cpu().numpy().view("uint32")
 
 
+def test_pcg64(seeds, draws):
+    """[n][draws] uint64 outputs of np.random.PCG64(np.random.SeedSequence(seed)) computed on the device."""
+    import numpy as np
+    sd = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64)).to(_dev())
+    out = torch.empty(len(sd), draws, dtype=torch.int64, device=_dev())
+    call("prl_test_pcg64", _ptr(sd), len(sd), draws, _ptr(out), _stream())
+    return out.cpu().numpy().view(np.uint64)
+
+
 def test_umma(mode, A, B, cfg=None):
     n_out = {0: 128, 1: 64, 2: 64, 3: 16}[mode] if cfg is None else cfg[2]
     D = torch.full((128, n_out), float("nan"), dtype=torch.float32, device=_dev())
@@ -94,6 +103,20 @@ class EnvState:
         obs = torch.empty(self.E, self.info["O"], dtype=torch.float32, device=_dev())
         call("prl_env_reset", self.code, self.E, seed, episode, _ptr(self.state), _ptr(self.elapsed),
              _ptr(self.terminal), _ptr(obs), _stream())
+        return obs
+
+    def reset_numpy(self, seeds=None):
+        """reset() from numpy's seeded stream (csrc/np_rng.cuh).  seeds: uint64-valued int64 CUDA tensor [E] -> every env's
+        generator is re-created as PCG64(SeedSequence(seed)); None -> the stored generators continue."""
+        if seeds is None and getattr(self, "np_rng", None) is None:
+            raise ValueError("reset_numpy(): the generators were never seeded")
+        if seeds is not None:
+            assert tuple(seeds.shape) == (self.E,)
+            if getattr(self, "np_rng", None) is None:
+                self.np_rng = torch.zeros(4, self.E, dtype=torch.int64, device=_dev())   # {state_hi, state_lo, inc_hi, inc_lo}
+        obs = torch.empty(self.E, self.info["O"], dtype=torch.float32, device=_dev())
+        call("prl_env_reset_numpy", self.code, self.E, _ptr(seeds, torch.int64) if seeds is not None else None,
+             _ptr(self.np_rng), _ptr(self.state), _ptr(self.elapsed), _ptr(self.terminal), _ptr(obs), _stream())
         return obs
 
     def set_state(self, state_aos):

@@ -311,6 +311,23 @@ def test_async_ppo_run_trains_cartpole(api):
     assert mean_len > 1.5 * first, (first, mean_len)  # the policy improves
 
 
+def test_env_vectorizer_seeded_reset_matches_seeded_numpy_envs(api):
+    """EnvVectorizer.reset(seed=s): env i starts where a gymnasium CartPole seeded with reset(seed=s+i) starts
+    (Generator(PCG64(SeedSequence(s+i))).uniform(-0.05, 0.05, 4), observation = float32(state)); the next unseeded
+    reset() - the reference's own call, AsyncPPO.py:48-62 - continues those generators."""
+    AsyncTools, _, prl = api
+    E, s = 37, 2024
+    vec = AsyncTools.AsyncPPO.EnvVectorizer(prl.make("CartPole-v1"), num_envs=E)
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s + i))) for i in range(E)]
+    obs, infos = vec.reset(seed=s)
+    assert len(infos) == E
+    assert np.array_equal(bits(obs), bits(np.stack([g.uniform(-0.05, 0.05, size=(4,)) for g in gens]).astype(np.float32)))
+    obs, _ = vec.reset()
+    assert np.array_equal(bits(obs), bits(np.stack([g.uniform(-0.05, 0.05, size=(4,)) for g in gens]).astype(np.float32)))
+    with pytest.raises(ValueError):
+        vec.reset(seed=[1, 2, 3])
+
+
 def test_checkpoint_round_trip_uses_reference_keys(api, tmp_path):
     P = api["PPO"]
     a = P.PPO(is_continuous=False, observ_dim=6, action_dim=3, use_RND=True)

@@ -114,6 +114,45 @@ def run_taped_rollout(ops, env_id, init_state, tape, T):
                 scores=scores.cpu().numpy(), terminal=info_env.terminal.cpu().numpy())
 
 
+def test_device_pcg64_equals_numpy(ops):
+    """np.random.PCG64(np.random.SeedSequence(seed)) on the device (csrc/np_rng.cuh): raw 64-bit outputs, bit-exact."""
+    seeds = [0, 1, 42, 2 ** 31 - 1, 2 ** 32, 2 ** 32 + 1, 2 ** 63 + 12345, 2 ** 64 - 1] + list(range(1234, 1234 + 300))
+    got = ops.test_pcg64(seeds, 16)
+    want = np.stack([np.random.PCG64(np.random.SeedSequence(s)).random_raw(16) for s in seeds])
+    assert np.array_equal(got, want)
+
+
+# reset boxes as gymnasium passes them to Generator.uniform (recalled; SURVEY.md section 8c): (low, high, size, float32 cast)
+NP_RESET = {
+    "CartPole-v1": lambda g: g.uniform(low=-0.05, high=0.05, size=(4,)),
+    "Pendulum-v1": lambda g: g.uniform(low=-np.array([np.pi, 1.0]), high=np.array([np.pi, 1.0])),
+    "Acrobot-v1": lambda g: g.uniform(low=-0.1, high=0.1, size=(4,)).astype(np.float32).astype(np.float64),
+    "MountainCar-v0": lambda g: np.array([g.uniform(low=-0.6, high=-0.4), 0.0]),
+}
+
+
+@pytest.mark.parametrize("env_id", list(ENVS.values()))
+def test_seeded_reset_equals_numpy_generators(ops, env_id):
+    """EnvState.reset_numpy: E envs seeded like `env.reset(seed=s_e)` start from numpy's own draws, bit for bit, and two
+    further resets continue every env's generator (ragged E: not a multiple of the block size)."""
+    E = 1000
+    seeds = np.arange(E, dtype=np.uint64) * np.uint64(7919) + np.uint64(2 ** 40 + 5)
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(s)))) for s in seeds]
+    sim = ops.EnvState(env_id, E)
+    with pytest.raises(ValueError):
+        sim.reset_numpy()
+    for k in range(3):
+        obs = sim.reset_numpy(dev(seeds.view(np.int64)) if k == 0 else None)
+        want = np.stack([NP_RESET[env_id](g) for g in gens])
+        got = sim.get_state().cpu().numpy()
+        assert np.array_equal(bits(got), bits(want)), (env_id, k)
+        assert obs.shape == (E, sim.info["O"]) and int(sim.terminal.sum()) == 0 and int(sim.elapsed.sum()) == 0
+    # re-seeding restarts the streams
+    sim.reset_numpy(dev(seeds.view(np.int64)))
+    g0 = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seeds[0]))))
+    assert np.array_equal(bits(sim.get_state().cpu().numpy()[0]), bits(NP_RESET[env_id](g0)))
+
+
 @pytest.mark.parametrize("key", list(ENVS))
 def test_fused_rollout_matches_reference_worker_golden(ops, golden, key):
     """Device worker() vs the REAL reference's AsyncPPO.worker (tests/golden): flat env-major buffer bit-exact."""

@@ -158,3 +158,22 @@ def test_two_rank_gloo_plumbing(tmp_path):
                         "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_np_rng_header_equals_numpy_on_the_host(tmp_path):
+    """csrc/np_rng.cuh compiled as host C++: PCG64(SeedSequence(seed)) raw outputs and doubles equal numpy's, bit for bit."""
+    import ctypes as C
+
+    so = str(tmp_path / "np_rng_check.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-D__host__=", "-D__device__=", "-I", os.path.join(PKG, "csrc"),
+                           os.path.join(ROOT, "tests", "host", "np_rng_check.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    seeds = np.array([0, 1, 42, 2 ** 32, 2 ** 63 + 12345, 2 ** 64 - 1] + list(range(1234, 1334)), dtype=np.uint64)
+    n, draws = len(seeds), 12
+    raw = np.zeros((n, draws), np.uint64)
+    uni = np.zeros((n, draws), np.float64)
+    lib.np_rng_check(seeds.ctypes.data_as(C.c_void_p), n, draws, raw.ctypes.data_as(C.c_void_p), uni.ctypes.data_as(C.c_void_p))
+    for i, s in enumerate(seeds):
+        bg = np.random.PCG64(np.random.SeedSequence(int(s)))
+        assert np.array_equal(raw[i], bg.random_raw(draws)), int(s)
+        assert np.array_equal(uni[i], np.random.Generator(bg).random(draws)), int(s)

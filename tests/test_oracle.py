@@ -176,3 +176,28 @@ def test_reference_float32_update_is_conditioned_at_1e5(golden):
     d = np.abs(oppo.flatten(p, cont).numpy() - g["post_flat"].astype(np.float64))
     ok = d <= 1e-5 * np.abs(g["post_flat"]) + 2e-6
     assert 2e-6 < d.max() < 3e-5 and 0.999 <= ok.mean() < 1.0, (d.max(), ok.mean())
+
+
+def test_numpy_seeded_reset_stream_restatement():
+    """oracle/np_rng.py (SeedSequence -> PCG64 -> Generator.uniform in plain integers) against numpy itself - the
+    implementation a seeded gymnasium env draws its reset state from; csrc/np_rng.cuh is the same code on the device."""
+    from oracle import np_rng as R
+
+    for seed in [0, 1, 42, 2 ** 31 - 1, 2 ** 32, 2 ** 63 + 12345, 2 ** 64 - 1] + list(range(1234, 1264)):
+        ss = np.random.SeedSequence(seed)
+        pool = R.seed_sequence_pool(seed)
+        assert [int(x) for x in ss.pool] == pool
+        assert [int(x) for x in ss.generate_state(4, np.uint64)] == R.generate_state_u64(pool, 4)
+        bg = np.random.PCG64(ss)
+        state, inc = R.pcg64_seed(seed)
+        assert (bg.state["state"]["state"], bg.state["state"]["inc"]) == (state, inc)
+        g = np.random.Generator(bg)
+        want = g.uniform(-0.05, 0.05, size=(4,))
+        for k in range(4):
+            state, u = R.uniform(state, inc, -0.05, 0.05)
+            assert u == want[k]
+        hi = np.array([np.pi, 1.0])
+        want = g.uniform(-hi, hi)
+        for k in range(2):
+            state, u = R.uniform(state, inc, -float(hi[k]), float(hi[k]))
+            assert u == want[k]
