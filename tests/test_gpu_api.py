@@ -315,7 +315,7 @@ def test_env_vectorizer_seeded_reset_matches_seeded_numpy_envs(api):
     """EnvVectorizer.reset(seed=s): env i starts where a gymnasium CartPole seeded with reset(seed=s+i) starts
     (Generator(PCG64(SeedSequence(s+i))).uniform(-0.05, 0.05, 4), observation = float32(state)); the next unseeded
     reset() - the reference's own call, AsyncPPO.py:48-62 - continues those generators."""
-    AsyncTools, _, prl = api
+    AsyncTools, prl = api["AsyncTools"], api["prl"]
     E, s = 37, 2024
     vec = AsyncTools.AsyncPPO.EnvVectorizer(prl.make("CartPole-v1"), num_envs=E)
     gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(s + i))) for i in range(E)]
