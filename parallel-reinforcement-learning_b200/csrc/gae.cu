@@ -9,6 +9,8 @@
 // strictly sequential WITHIN one, in the reference's operation order.  Two forms:
 //   prl_gae_columns  time-major [T][E]: one env per thread walking t backwards - fully coalesced across envs.
 //   prl_gae          flat env-major [N] (the compute_gae signature): one segment per lane, staged through shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace prl {
@@ -140,7 +142,7 @@ __device__ __forceinline__ int fpad(int i) { return i + (i >> 5) + (i >> 7); }
 constexpr int FWP = FW + FW / 32 + FW / 128 + 2;
 constexpr int FNQ = (FW / 4 + FT - 1) / FT;                       // float4 groups per thread (4); group q = tid + k FT
 constexpr int FQS = 4 * FT + (4 * FT) / 32 + (4 * FT) / 128;      // shared-memory words between a thread's groups
-static_assert(FH == 128 && FT == 256 && FNQ * (FT / 32) <= 32, "the block bookkeeping below relies on these");
+static_assert(FH == 128 && FT == 256 && FNQ * (FT / 32) == 32, "the block bookkeeping below relies on these (all 32 block counts are written)");
 
 // x of one element: delta, or gae for a segment end (gae_{t+1} = 0 there; the products keep the reference's NaN / -0 behaviour)
 __device__ __forceinline__ float gae_x(float r, float d, float v, float nv, bool is_end, float g, float gl) {
@@ -153,6 +155,22 @@ __device__ __forceinline__ void gae_walk(float *sx, int t, int s, float gl, floa
     while (t >= s) {
         const int b0 = t & ~31, lo = max(s, b0);       // one 32-element block: contiguous in shared memory
         float *px = sx + fpad(b0) - b0;
+        if (lo == b0 && t == b0 + 31) {
+            // a whole block: 32 independent loads in flight, the chain retires from registers, then 32 stores (the chain
+            // never waits for shared memory; the 8-element form below interleaves a load latency into every batch)
+            float x[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) x[u] = px[b0 + u];
+#pragma unroll
+            for (int u = 31; u >= 0; --u) {
+                gae = __fadd_rn(x[u], __fmul_rn(gl, gae));
+                x[u] = gae;
+            }
+#pragma unroll
+            for (int u = 0; u < 32; ++u) px[b0 + u] = x[u];
+            t = b0 - 1;
+            continue;
+        }
         for (; t - 7 >= lo; t -= 8) {
             float x8[8];
 #pragma unroll
@@ -350,6 +368,221 @@ k_gae_flat(const float *__restrict__ rewards, const float *__restrict__ dones, c
     }
 }
 
+// ---- flat form, persistent with prefetch ---------------------------------------------------------------------------
+// Same algorithm, same shared-memory walk and the same bits as k_gae_flat; what changes is how the chunk arrives.
+// k_gae_flat holds its 12 float4 loads in registers, so a CTA has loads in flight only during the first phase of its
+// life (measured: ~45 % of the copy peak - too few bytes in flight per SM).  Here a CTA is persistent (3 per SM), the raw
+// rewards / dones / values window of its NEXT chunk is fetched by 16-byte cp.async copies into a separate shared-memory
+// staging area (no registers) as soon as the current chunk has been consumed from it, and the copies fly while the CTA
+// compacts, walks and stores the current chunk: ~38 KB per CTA, ~115 KB per SM are in flight all the time.
+// The staging area doubles as k_gae_flat's sd[] (edge chunks, long-segment windows): a prefetch is only issued when
+// nobody uses it in that role any more.
+constexpr int FRAW = FW + 4;   // + the value after the window (only word 0 of the 4 is used)
+constexpr size_t GAE_PF_SMEM = (size_t)(3 * FRAW + 2 * FWP) * 4 + FL * 2 + 16;
+static_assert((3 * FRAW) * 4 >= FWP * 4, "staging area too small to stand in for sd[]");
+
+__global__ void __launch_bounds__(FT, 3)
+k_gae_flat_pf(const float *__restrict__ rewards, const float *__restrict__ dones, const float *__restrict__ values,
+              const float *__restrict__ next_value_ptr, int64_t N, int L, float g, float gl, float *__restrict__ returns) {
+    extern __shared__ __align__(16) float dyn[];
+    float *raw = dyn, *sd = dyn;                         // raw: [3][FRAW] rewards, dones, values of the window, unpadded
+    float *sx = dyn + 3 * FRAW, *sv = sx + FWP;
+    uint16_t *ends = reinterpret_cast<uint16_t *>(sv + FWP);
+    __shared__ int bcnt[32], s_hend;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t nchunks = (N + L - 1) / L;
+    const int W4 = (FH + L) / 4;   // float4 groups of a full window (L % 4 == 0)
+    const float nv_end = next_value_ptr ? *next_value_ptr : values[N - 1];
+    auto interior = [&](int64_t ch) { return ch > 0 && ch < nchunks && (ch + 1) * L <= N; };
+    auto prefetch = [&](int64_t ch) {   // the whole window of an interior chunk; every thread commits one group
+        if (interior(ch)) {
+            const int64_t b = ch * L - FH;
+#pragma unroll
+            for (int k = 0; k < FNQ; ++k) {
+                const int q = tid + k * FT;
+                if (q < W4) {
+                    cp_async16(raw + 4 * q, rewards + b + 4 * q);
+                    cp_async16(raw + FRAW + 4 * q, dones + b + 4 * q);
+                    cp_async16(raw + 2 * FRAW + 4 * q, values + b + 4 * q);
+                }
+            }
+            if (tid == 0 && b + 4 * W4 < N) cp_async4(raw + 2 * FRAW + 4 * W4, values + b + 4 * W4);
+        }
+        cp_async_commit();
+    };
+    prefetch(blockIdx.x);
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t c0 = chunk * L, base = c0 - FH;   // window element i = global element base + i
+        const int len = (int)min((int64_t)L, N - c0), lim = FH + len;
+        const int h0 = base < 0 ? (int)-base : 0;                       // first valid window element
+        const int ilast = N - 1 - base < (int64_t)lim ? (int)(N - 1 - base) : -1;   // window index of the very last transition
+        const float nv_last = ilast >= 0 ? nv_end : 0.f;
+        unsigned nib[FNQ];   // bit c of nib[k]: element 4 q + c (q = tid + k FT) is a segment end
+#pragma unroll
+        for (int k = 0; k < FNQ; ++k) nib[k] = 0;
+        cp_async_wait<0>();
+        __syncthreads();     // the window has landed; everybody is done with the previous chunk's sx / sv / ends
+        if (interior(chunk)) {
+            const float4 *gr = reinterpret_cast<const float4 *>(raw), *gd = reinterpret_cast<const float4 *>(raw + FRAW),
+                         *gv = reinterpret_cast<const float4 *>(raw + 2 * FRAW);
+            const int p0 = fpad(4 * tid);
+#pragma unroll
+            for (int k = 0; k < FNQ; ++k) {
+                const int q = tid + k * FT;
+                if (q < W4) {
+                    const float4 a = gr[q], bq = gd[q], c = gv[q];
+                    const int i = 4 * q, p = p0 + k * FQS;
+                    const float vn = i + 3 == ilast ? nv_last : raw[2 * FRAW + i + 4];
+                    const bool e0 = bq.x != 0.f, e1 = bq.y != 0.f, e2 = bq.z != 0.f, e3 = bq.w != 0.f || i + 3 == ilast;
+                    sx[p] = gae_x(a.x, bq.x, c.x, c.y, e0, g, gl);
+                    sx[p + 1] = gae_x(a.y, bq.y, c.y, c.z, e1, g, gl);
+                    sx[p + 2] = gae_x(a.z, bq.z, c.z, c.w, e2, g, gl);
+                    sx[p + 3] = gae_x(a.w, bq.w, c.w, vn, e3, g, gl);
+                    sv[p] = c.x; sv[p + 1] = c.y; sv[p + 2] = c.z; sv[p + 3] = c.w;
+                    nib[k] = (e0 ? 1u : 0u) | (e1 ? 2u : 0u) | (e2 ? 4u : 0u) | (e3 ? 8u : 0u);
+                }
+            }
+        } else {
+            // ---- first / last chunk: scalar staging (sd[] = the staging area; nothing is in flight into it)
+            for (int i = h0 + tid; i < lim; i += FT) {
+                const int p = fpad(i);
+                sx[p] = rewards[base + i]; sd[p] = dones[base + i]; sv[p] = values[base + i];
+            }
+            __syncthreads();
+            for (int i = h0 + tid; i < lim; i += FT) {
+                const int p = fpad(i);
+                const float d = sd[p];
+                const float nv = i == ilast ? nv_last : (i + 1 < lim ? sv[fpad(i + 1)] : values[base + i + 1]);
+                const bool is_end = d != 0.f || i == ilast;
+                sx[p] = gae_x(sx[p], d, sv[p], nv, is_end, g, gl);
+                sd[p] = is_end ? 1.f : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < FNQ; ++k) {
+                const int i = 4 * (tid + k * FT);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    if (i + cc >= h0 && i + cc < lim && sd[fpad(i + cc)] != 0.f) nib[k] |= 1u << cc;
+            }
+        }
+        // ---- compaction of the segment ends, ascending (as k_gae_flat)
+        int pre[FNQ];
+        {
+            int hend = -1;
+#pragma unroll
+            for (int k = 0; k < FNQ; ++k) {
+                const int mine = __popc(nib[k]);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                pre[k] = incl - mine;
+                if (lane == 31) bcnt[8 * k + w] = (k == 0 && w == 0) ? 0 : incl;
+                if (k == 0 && w == 0) {   // the halo: its last end
+                    const unsigned any = __ballot_sync(0xffffffffu, nib[0] != 0);
+                    if (any) {
+                        const int hl = 31 - __clz(any);
+                        const unsigned hn = __shfl_sync(0xffffffffu, nib[0], hl);
+                        hend = 4 * hl + 31 - __clz(hn);
+                    }
+                }
+            }
+            if (tid == 0) s_hend = hend;
+        }
+        __syncthreads();     // bcnt, s_hend visible; the staging area has been consumed by everybody
+        int excl, ns;
+        {
+            const int v = bcnt[lane];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            excl = incl - v;
+            ns = __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const int hend = s_hend;
+        const int s_first = hend >= 0 ? hend + 1 : h0;
+        const bool open = ns > 0 && hend < 0 && base > 0;   // the first segment begins before the window (CTA-uniform)
+        const int64_t next = chunk + gridDim.x;
+        if (!open) prefetch(next);   // flies during the walk and the stores
+        if (ns == 0) continue;       // no segment ends here: a later chunk owns everything in this one
+#pragma unroll
+        for (int k = 0; k < FNQ; ++k) {
+            const int off = __shfl_sync(0xffffffffu, excl, 8 * k + w) + pre[k];
+            if ((k == 0 && w == 0) || nib[k] == 0) continue;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                if (nib[k] >> cc & 1) ends[off + __popc(nib[k] & ((1u << cc) - 1))] = (uint16_t)(4 * (tid + k * FT) + cc);
+        }
+        __syncthreads();
+        float gae_open = 0.f;
+        // ---- one segment per thread
+        for (int k = tid; k < ns; k += FT) {
+            const int e = ends[k], s = k ? ends[k - 1] + 1 : s_first;
+            float gae = sx[fpad(e)];
+#ifndef GAE_NOWALK
+            gae_walk(sx, e - 1, s, gl, gae);
+#endif
+            if (k == 0) gae_open = gae;
+        }
+        __syncthreads();
+        {   // returns of [s_first, last end]: coalesced
+            const int last = ends[ns - 1];
+            int i = s_first + tid;
+            const float *px = sx + fpad(i), *pv = sv + fpad(i);
+            float *go = returns + base + i;
+            constexpr int ps = FT + FT / 32 + FT / 128;
+            for (; i + 3 * FT <= last; i += 4 * FT, px += 4 * ps, pv += 4 * ps, go += 4 * FT) {
+                const float a0 = __fadd_rn(px[0], pv[0]), a1 = __fadd_rn(px[ps], pv[ps]), a2 = __fadd_rn(px[2 * ps], pv[2 * ps]),
+                            a3 = __fadd_rn(px[3 * ps], pv[3 * ps]);
+                __stcs(go, a0); __stcs(go + FT, a1); __stcs(go + 2 * FT, a2); __stcs(go + 3 * FT, a3);
+            }
+            for (; i <= last; i += FT, px += ps, pv += ps, go += FT) __stcs(go, __fadd_rn(*px, *pv));
+        }
+        if (!open) continue;
+        // ---- the rest of a first segment longer than the halo (as k_gae_flat: warp 0, windows in sd[]); the prefetch of
+        // the next chunk waits until these windows are done with the staging area
+        if (w == 0) {
+            float gae = __shfl_sync(0xffffffffu, gae_open, 0);
+            float nv = values[base + s_first];    // value of the element after the window's top
+            for (int64_t top = base; top > 0;) {
+                const int cnt2 = (int)min((int64_t)FX, top);
+                const int64_t w0 = top - cnt2;
+                int he = -1;
+                __syncwarp();
+                for (int it = 0; it * 32 < cnt2; ++it) {
+                    const int i = it * 32 + lane;
+                    const bool in = i < cnt2;
+                    const float dd = in ? dones[w0 + i] : 0.f;
+                    if (in) {
+                        const float v = values[w0 + i];
+                        const float vn = i + 1 < cnt2 ? values[w0 + i + 1] : nv;
+                        sd[fpad(i)] = gae_x(rewards[w0 + i], 0.f, v, vn, false, g, gl);
+                        sd[FWP / 2 + fpad(i)] = v;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, in && dd != 0.f);
+                    if (bal) he = it * 32 + 31 - __clz(bal);
+                }
+                __syncwarp();
+                if (lane == 0) gae_walk(sd, cnt2 - 1, he + 1, gl, gae);
+                __syncwarp();
+                for (int i = he + 1 + lane; i < cnt2; i += 32) returns[w0 + i] = __fadd_rn(sd[fpad(i)], sd[FWP / 2 + fpad(i)]);
+                if (he >= 0) break;
+                nv = values[w0];
+                top = w0;
+            }
+        }
+        __syncthreads();
+        prefetch(next);
+    }
+    cp_async_wait<0>();
+}
+
 // ---- advantage normalisation -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_adv_stats(const float *__restrict__ returns, const float *__restrict__ values, int64_t N, double *__restrict__ stats) {
@@ -422,12 +655,25 @@ int prl_gae(const float *rewards, const float *dones, const float *values, const
     if (N == 0) return PRL_OK;
     PRL_REQUIRE(rewards && dones && values && returns, "prl_gae: null pointer");
     // 46 KB of static shared memory per CTA: ask for the largest carve-out so that 3-4 of them fit per SM
-    static const bool carve = (cudaFuncSetAttribute(k_gae_flat<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
-                               cudaFuncSetAttribute(k_gae_flat<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
+    static const bool carve = (cudaFuncSetAttribute(k_gae_flat<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
     (void)carve;
     const bool vec = (((uintptr_t)rewards | (uintptr_t)dones | (uintptr_t)values) & 15) == 0;
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
-    if (vec) k_gae_flat<true><<<cdiv(N, FL), FT, 0, (cudaStream_t)stream>>>(rewards, dones, values, next_value_ptr, N, g, gl, returns);
+    if (vec) {
+        static const bool attr = (cudaFuncSetAttribute(k_gae_flat_pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GAE_PF_SMEM), true);
+        (void)attr;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // persistent CTAs, 3 per SM.  Chunk length: FL once there is more than one round of chunks (measured: shorter
+        // chunks that even out the rounds are slower - 47.7 us at L = 2816 against 42.5 us at L = 3072 for 8.4 M
+        // transitions); a single partial round is spread over all CTAs in multiples of 128.
+        const int64_t ctas = (int64_t)sms * 3;
+        int L = FL;
+        if (N < ctas * FL) L = (int)max((int64_t)512, min((int64_t)FL, ((N + ctas - 1) / ctas + 127) / 128 * 128));
+        const int grid = (int)min((int64_t)cdiv(N, L), ctas);
+        k_gae_flat_pf<<<grid, FT, GAE_PF_SMEM, (cudaStream_t)stream>>>(rewards, dones, values, next_value_ptr, N, L, g, gl, returns);
+    }
     else k_gae_flat<false><<<cdiv(N, FL), FT, 0, (cudaStream_t)stream>>>(rewards, dones, values, next_value_ptr, N, g, gl, returns);
     return check_launch("k_gae_flat");
 }

@@ -291,6 +291,27 @@ def test_gae_flat_halo_windows_and_unaligned_views(ops):
     assert np.array_equal(bits(got.cpu().numpy()), bits(want))
 
 
+def test_gae_flat_balanced_chunk_lengths(ops):
+    """The persistent flat kernel picks its chunk length from N (every CTA walks the same number of chunks), so chunk and
+    halo edges fall at arbitrary multiples of 4: sizes from one partial round to several rounds, ragged and equal-length
+    episodes, short and very long segments."""
+    rng = np.random.default_rng(77)
+    for N, kind in [(250_000, "ragged"), (1_000_003, "ragged"), (1_400_000, 128), (2_000_001, 500), (3_000_000, "long"), (4_099_072, 200)]:
+        d = np.zeros(N, np.float32)
+        if kind == "ragged":
+            lens = rng.integers(1, 300, N // 100)
+            e = np.cumsum(lens) - 1
+            d[e[e < N]] = 1.0
+        elif kind == "long":
+            d[rng.integers(0, N, 40)] = 1.0       # segments of ~75 000 transitions: dozens of chunks each
+        else:
+            d[kind - 1::kind] = 1.0
+        r = rng.standard_normal(N).astype(np.float32); v = rng.standard_normal(N).astype(np.float32)
+        want = cref.gae(r, d, v, v[-1], 0.995, 0.95)
+        got = ops.gae(dev(r), dev(d), dev(v), 0.995, 0.95)
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want)), (N, kind)
+
+
 @pytest.mark.parametrize("T,E", [(64, 5000), (128, 4099), (37, 30), (200, 1024)])
 def test_gae_columns_bit_exact_and_equal_to_flat(ops, T, E):
     """Ring-buffered kernel (E % 4 == 0) and the plain one (any E), ragged and full-length columns."""
