@@ -660,8 +660,7 @@ int prl_gae(const float *rewards, const float *dones, const float *values, const
     const bool vec = (((uintptr_t)rewards | (uintptr_t)dones | (uintptr_t)values) & 15) == 0;
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     if (vec) {
-        static const bool attr = (cudaFuncSetAttribute(k_gae_flat_pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GAE_PF_SMEM), true);
-        (void)attr;
+        PRL_CUDA(cudaFuncSetAttribute(k_gae_flat_pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GAE_PF_SMEM));   // per device
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
