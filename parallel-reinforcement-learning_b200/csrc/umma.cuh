@@ -87,6 +87,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // the GPU); the caller records the failure and carries on.
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (int it = 0; it < (1 << 22); ++it) {
         uint32_t ok;
         asm volatile(

@@ -9,15 +9,32 @@
 // features 16q..16q+15 = two GroupNorm groups), so every per-row array is 16 wide and lives in registers.
 // Everything that contracts over features or over rows runs as tcgen05.mma (kind::f16 on bf16x3 split operands, fp32
 // accumulators in tensor memory), issued by one elected lane of warp 16, which does nothing else: the compute warps hand
-// it staged operands through named barriers (arrive, no wait) and only ever wait for MMA completion (mbarriers):
-//     forward   Z[r][(h,j)]  = sum_k F[r][k] W1_h[j][k]          M=128 N=128 K=64    (both heads in one GEMM)
-//     dgrad     DF[r][k]    += sum_j DZ_h[r][j] W1_h[j][k]       M=128 N=64  K=64    (B = MN-major view of the same W1 bytes)
+// it staged operands through mbarriers (arrive, no wait) and only ever wait for MMA completion (mbarriers):
+//     forward   Z[r][(h,j)]  = sum_k F[r][k] W1c_h[j][k]         M=128 N=64  K=64    (per head)
+//     dgrad     DF[r][k]    += sum_j DZ_h[r][j] W1c_h[j][k]      M=128 N=64  K=64    (B = MN-major view of the same W1 bytes)
 //     wgrad     DW_h[j][k]  += sum_r DZ_h[r][j] F[r][k]          M=128 N=64  K=128   (A, B = MN-major views of the same DZ / F bytes)
 //     wgrad0    DW0[j][i]   += sum_r DZ0[r][j] X[r][i]           M=128 N=16  K=128
 // The weight-gradient accumulators stay in tensor memory across ALL tiles of the CTA and are read out once.
+//
 // What remains on the CUDA cores are the row-wise nonlinearities (GroupNorm, SiLU, softmax / loss and their backward)
-// and the narrow column sums (GroupNorm affine and output-layer gradients), done as warp butterfly reductions into
-// per-warp register accumulators that are combined once at the end.
+// and the narrow column sums (GroupNorm affine and output-layer gradients).  That part is written for issue slots, the
+// resource that bounds the kernel (ncu, round 1: 41 M warp instructions per 65 536-row launch, issue 33 % busy, top stall
+// "no instruction" on 229 KB of SASS):
+//   * every element-wise step works on float2 feature pairs (FFMA2 / FADD2 / FMUL2, sm_100: half the instructions to fetch
+//     and decode; measured on B200 a packed instruction occupies the FMA pipe for two issue cycles, so this buys code size,
+//     not issue slots);
+//   * GroupNorm without a mean pass: the hidden-layer weights are staged CENTRED per GroupNorm group
+//     (W1c[j][:] = W1[j][:] - mean over the 8 rows j' of j's group), so the GEMM delivers z - mean_group(z) directly.
+//     GroupNorm is invariant to that shift, its input gradient has zero group mean, so dgrad may use the same centred
+//     bytes and the weight gradient is unchanged;
+//   * column sums as warp butterfly reductions into per-lane REGISTER accumulators that live across all tiles of the CTA
+//     and are combined once per launch in a fixed order (bit-reproducible).  (Measured and rejected: a per-warp
+//     shared-memory transposition instead of the shuffles - 2 KB in and 2 KB out per quantity and warp is shared-memory
+//     bandwidth the tensor core needs for its operands: 1.08 ms against 0.86 ms in tools/micro/ubench.cu);
+//   * nothing is recomputed: what the backward needs of a forward stays in registers or is parked in this thread's
+//     lane of tensor memory (tcgen05.st / tcgen05.ld: 1 instruction per 16 values);
+//   * the four threads of a row exchange their partial head outputs through shared memory behind a 128-thread named
+//     barrier per row quarter (the quarters run independently between MMA hand-offs).
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,8 +50,11 @@ constexpr int PIECE = 8 * CHUNK;     // one bf16 piece of a [128][64] matrix: 8 
 constexpr int XPIECE = 2 * CHUNK;    // one bf16 piece of the [128][16] input matrix
 constexpr int TC_MAX_O = 16, TC_MAX_A = 8;
 
-// tensor-memory columns
-constexpr uint32_t TM_Z = 0, TM_DF = 128, TM_DW = 192 /* + 64 h */, TM_DW0 = 320, TM_COLS = 512;
+// tensor-memory columns.  DF (trunk-activation gradient) reuses the actor's Z columns: the actor epilogue has read Z_0
+// before it hands DZ_0 over, and only then is the first dgrad MMA issued.  ZH0 / DS0 / HJ are per-thread parking space
+// (lane = row, 16 columns per feature quarter): the trunk's zhat and SiLU derivative for the trunk backward, a head's
+// SiLU output for its dW2.
+constexpr uint32_t TM_Z = 0, TM_DF = 0, TM_DW = 128 /* + 64 h */, TM_DW0 = 256, TM_ZH0 = 288, TM_DS0 = 352, TM_HJ = 416, TM_COLS = 512;
 
 __host__ __device__ inline int tc_small_floats(const PolicyLayout &L) {
     int n = L.O * HID + 2 * HID;
@@ -42,21 +62,44 @@ __host__ __device__ inline int tc_small_floats(const PolicyLayout &L) {
     return n;
 }
 __host__ __device__ inline int tc_num_q(const PolicyLayout &L) { return 2 + 2 + L.head[0].out + 2 + L.head[1].out; }
+// W (3 pieces) | F (3) | DZ (3 + a zero piece) | X (3 small) | small parameters | partial head outputs [4 q][128][NA] + [4 q][128]
 __host__ __device__ inline size_t tc_smem_bytes(const PolicyLayout &L, int NA) {
-    return 1024 + 3 * PIECE + 3 * PIECE + 4 * PIECE + 3 * XPIECE + (size_t)tc_small_floats(L) * 4 + (size_t)4 * TC_ROWS * NA * 4 +
-           (size_t)4 * tc_num_q(L) * HID * 4 + 256;
+    return 3 * PIECE + 3 * PIECE + 4 * PIECE + 3 * XPIECE + (size_t)((tc_small_floats(L) + 3) & ~3) * 4 + (size_t)4 * TC_ROWS * (NA + 1) * 4 + 128;
 }
 
 // ---- small math ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_sigmoid(float y) { return __fdividef(1.0f, 1.0f + __expf(-y)); }
+typedef float2 f2;
+__device__ __forceinline__ f2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / (1 + exp(-y)) on a feature pair: FMUL2, 2 x MUFU.EX2, FADD2, 2 x MUFU.RCP (2 ulp; saturates cleanly at both ends)
+__device__ __forceinline__ f2 sigmoid2(f2 y) {
+    const f2 t = mul2(y, dup2(-1.4426950408889634f));
+    const f2 d = add2(mk2(ex2_approx(t.x), ex2_approx(t.y)), dup2(1.0f));
+    return mk2(rcp_approx(d.x), rcp_approx(d.y));
+}
+__device__ __forceinline__ float fast_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_log(float x) { return lg2_approx(x) * 0.6931471805599453f; }
 
-// write 16 fp32 values (features 16q..16q+15 of row r) as three bf16 pieces: chunks 2q, 2q+1 of a [128][64] piece triple
-__device__ __forceinline__ void store_pieces16(unsigned char *base, int r, int q, const float (&v)[TC_W]) {
+// write 16 fp32 values (features 16q..16q+15 of row r, as 8 pairs) as three bf16 pieces: chunks 2q, 2q+1 of a [128][64] piece triple
+__device__ __forceinline__ void store_pieces16(unsigned char *base, int r, int q, const f2 (&v)[8]) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         uint32_t q0[4], q1[4], q2[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_bf16x3(v[8 * c + 2 * i], v[8 * c + 2 * i + 1], q0[i], q1[i], q2[i]);
+        for (int i = 0; i < 4; ++i) {
+            const f2 x = v[4 * c + i];
+            q0[i] = pack_bf16x2(x.x, x.y);
+            const f2 r0 = fma2(mk2(__uint_as_float(q0[i] << 16), __uint_as_float(q0[i] & 0xffff0000u)), dup2(-1.0f), x);   // exact
+            q1[i] = pack_bf16x2(r0.x, r0.y);
+            const f2 r1 = fma2(mk2(__uint_as_float(q1[i] << 16), __uint_as_float(q1[i] & 0xffff0000u)), dup2(-1.0f), r0);  // exact
+            q2[i] = pack_bf16x2(r1.x, r1.y);
+        }
         unsigned char *p = base + (2 * q + c) * CHUNK + r * 16;
         *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
         *reinterpret_cast<uint4 *>(p + PIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
@@ -80,66 +123,57 @@ __device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3,
     c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
     return c0;
 }
-// column sums of the thread's two groups, accumulated into the warp's 16-float slot of the shared accumulator array
-// (slot[8 g + f(lane)] += total; one of the four lanes holding a feature does the update)
-__device__ __forceinline__ void colsum16(const float (&v)[TC_W], float *slot) {
-    const float c0 = colsum8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-    const float c1 = colsum8(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
-    const int lane = threadIdx.x & 31;
-    if ((lane & 3) == 0) {
-        const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        slot[f] += c0;
-        slot[8 + f] += c1;
-    }
+// column sums of the thread's 16 features (8 pairs) over the warp's 32 rows, added to the lane's register accumulators:
+// acc.x += total of feature f(lane) of group 0, acc.y += the same of group 1 (all four lanes holding a feature keep it: no
+// divergent update, nothing in memory; the accumulators live across all tiles of the CTA)
+__device__ __forceinline__ void colsum16(const f2 (&v)[8], f2 &acc) {
+    acc.x += colsum8(v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y);
+    acc.y += colsum8(v[4].x, v[4].y, v[5].x, v[5].y, v[6].x, v[6].y, v[7].x, v[7].y);
 }
 
-// GroupNorm on the thread's two groups: z -> zhat in place, rstd per group
-__device__ __forceinline__ void gn_normalize16(float (&z)[TC_W], float (&rstd)[2]) {
+// GroupNorm on the thread's two groups when the GEMM delivered z - mean_group(z) (centred weights): z -> zhat in place
+__device__ __forceinline__ void gn_normalize_centred(f2 (&z)[8], float (&rstd)[2]) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-        float m = 0.f;
+        f2 v = mul2(z[4 * g], z[4 * g]);
 #pragma unroll
-        for (int i = 0; i < GSIZE; ++i) m += z[g * GSIZE + i];
-        m *= (1.0f / GSIZE);
-        float v = 0.f;
-#pragma unroll
-        for (int i = 0; i < GSIZE; ++i) { const float d = z[g * GSIZE + i] - m; v = fmaf(d, d, v); }
-        const float r = rsqrtf(v * (1.0f / GSIZE) + GN_EPS);
+        for (int i = 1; i < 4; ++i) v = fma2(z[4 * g + i], z[4 * g + i], v);
+        const float r = rsqrtf(fmaf(v.x + v.y, 1.0f / GSIZE, GN_EPS));
         rstd[g] = r;
 #pragma unroll
-        for (int i = 0; i < GSIZE; ++i) z[g * GSIZE + i] = (z[g * GSIZE + i] - m) * r;
+        for (int i = 0; i < 4; ++i) z[4 * g + i] = mul2(z[4 * g + i], dup2(r));
     }
 }
 // dy -> dz in place: d = dy * gamma, dz = rstd * (d - mean(d) - zhat * mean(d * zhat)) per group
-__device__ __forceinline__ void gn_backward16(float (&d)[TC_W], const float (&zhat)[TC_W], const float (&rstd)[2], const float (&gamma)[TC_W]) {
+__device__ __forceinline__ void gn_backward16(f2 (&d)[8], const f2 (&zhat)[8], const float (&rstd)[2], const float *gamma16) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-        float m1 = 0.f, m2 = 0.f;
+        const float4 ga = *reinterpret_cast<const float4 *>(gamma16 + 8 * g), gb = *reinterpret_cast<const float4 *>(gamma16 + 8 * g + 4);
+        d[4 * g] = mul2(d[4 * g], mk2(ga.x, ga.y));
+        d[4 * g + 1] = mul2(d[4 * g + 1], mk2(ga.z, ga.w));
+        d[4 * g + 2] = mul2(d[4 * g + 2], mk2(gb.x, gb.y));
+        d[4 * g + 3] = mul2(d[4 * g + 3], mk2(gb.z, gb.w));
+        f2 s1 = add2(d[4 * g], d[4 * g + 1]), s2 = mul2(d[4 * g], zhat[4 * g]);
+        s1 = add2(s1, add2(d[4 * g + 2], d[4 * g + 3]));
 #pragma unroll
-        for (int i = 0; i < GSIZE; ++i) {
-            const int j = g * GSIZE + i;
-            d[j] *= gamma[j];
-            m1 += d[j];
-            m2 = fmaf(d[j], zhat[j], m2);
-        }
-        m1 *= (1.0f / GSIZE); m2 *= (1.0f / GSIZE);
+        for (int i = 1; i < 4; ++i) s2 = fma2(d[4 * g + i], zhat[4 * g + i], s2);
+        const float a = rstd[g];
+        const float c1 = -(s1.x + s1.y) * (1.0f / GSIZE) * a, c2 = -(s2.x + s2.y) * (1.0f / GSIZE) * a;
 #pragma unroll
-        for (int i = 0; i < GSIZE; ++i) {
-            const int j = g * GSIZE + i;
-            d[j] = rstd[g] * (d[j] - m1 - zhat[j] * m2);
-        }
+        for (int i = 0; i < 4; ++i) d[4 * g + i] = fma2(d[4 * g + i], dup2(a), fma2(zhat[4 * g + i], dup2(c2), dup2(c1)));
     }
 }
-__device__ __forceinline__ void load16(const float *src, float (&v)[TC_W]) {
+__device__ __forceinline__ void load16(const float *src, f2 (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 t = reinterpret_cast<const float4 *>(src)[i];
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        v[2 * i] = mk2(t.x, t.y); v[2 * i + 1] = mk2(t.z, t.w);
     }
 }
 
-// named barrier 1 = the 512 compute threads among themselves (the MMA warp never joins it)
+// named barrier 1 = the 512 compute threads among themselves (the MMA warp never joins it); 2 + rq = the four warps of row quarter rq
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void bar_quarter(int rq) { asm volatile("bar.sync %0, 128;" ::"r"(2 + rq) : "memory"); }
 // compute side of an "operands staged" hand-off to the MMA warp: make the shared-memory stores visible to the tensor core
 // (async proxy), then arrive on the hand-off mbarrier (count 512) without waiting
 __device__ __forceinline__ void staged(uint64_t *bar) {
@@ -200,37 +234,78 @@ __device__ __forceinline__ void issue_trunk_wgrad(const TcDesc &D, bool first_ti
     }
 }
 
-__device__ __forceinline__ void tmem_ld16w(uint32_t taddr, float (&v)[TC_W]) {
-    tmem_ld16(taddr, v);
-    tmem_ld_wait();
+// ---- tensor memory <-> registers, 16 columns of this thread's lane as 8 float pairs ----------------------------------------
+__device__ __forceinline__ void tmem_ld16_f2(uint32_t taddr, f2 (&v)[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = mk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
+// two loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2_f2(uint32_t ta, f2 (&a)[8], uint32_t tb, f2 (&b)[8]) {
+    uint32_t r[16], s[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(s[9]),
+          "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = mk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        b[i] = mk2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+    }
+}
+// park 16 values in this thread's lane (completes before the thread goes on: the same thread reads them back later)
+__device__ __forceinline__ void tmem_st16_f2(uint32_t taddr, const f2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        :
+        : "r"(taddr), "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)), "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)),
+          "r"(__float_as_uint(v[2].x)), "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)),
+          "r"(__float_as_uint(v[4].x)), "r"(__float_as_uint(v[4].y)), "r"(__float_as_uint(v[5].x)), "r"(__float_as_uint(v[5].y)),
+          "r"(__float_as_uint(v[6].x)), "r"(__float_as_uint(v[6].y)), "r"(__float_as_uint(v[7].x)), "r"(__float_as_uint(v[7].y))
+        : "memory");
 }
 
-// Fused optimiser tail (single-GPU path): after a grid-wide barrier every CTA reduces its slice of the parameters over
-// all CTAs' partial gradients (fixed order), a second barrier makes the squared-norm partials visible, then every CTA
-// applies clip_grad_norm_ + AdamW to its slice.  One launch per optimiser step instead of three.
+// Fused optimiser tail: every CTA writes its partial-gradient row and loss sums, then adds one to an arrival counter
+// (release); every CTA waits for the counter to reach the grid size (ONE word polled by one lane per CTA - polling a word
+// per producer from every CTA hot-spots a handful of L2 lines: measured 3 us per exchange), reduces its 64-parameter
+// slices over the CTAs' partial rows in a fixed order and publishes the squared norm of its slices as a tagged word.
+// The LEADER CTA (the last one: it owns no slice when the grid is larger than the slice count) collects those, and
+// publishes the clip coefficient as one tagged word that everybody else polls; then every CTA applies clip_grad_norm_ +
+// AdamW to its slices.  One launch per optimiser step instead of three; no grid barrier, no host-side reset.
 struct TcOptimizer {
     float *params_rw, *grad, *m, *v;          // params_rw == nullptr: gradient only (the reduction runs as a separate kernel)
     int64_t *clock;                           // {int64 step, double beta1^step, double beta2^step}
-    unsigned int *sync;                       // {arrival count, generation} of the grid barrier
-    double *sumsq;                            // [grid] squared-norm partials (unused by the fused step: tagged words instead)
-    unsigned long long *tagw;                 // [grid][8] tagged words: loss sums (3 doubles = 6 words), squared norm (2 words)
+    unsigned int *count;                      // arrival counter behind the partial rows (zero between launches: the leader CTA resets it)
+    unsigned long long *tagw;                 // [grid][2] tagged words: squared norm of the CTA's slices (a double in two halves)
+    unsigned long long *coefw;                // 2 tagged words published by the leader CTA: clip coefficient, total gradient norm
     double *norm_out;
     float lr, wd, max_norm;
     double *loss_out;                         // 4 doubles, accumulated
     double rows;
+    unsigned long long timeout_ns;            // bound of every cross-CTA / cross-GPU wait (wall clock, %globaltimer)
     // sharded runs: the gradient exchange happens inside this kernel over NVLink peer memory instead of an NCCL allreduce.
     // peers[r] = base of rank r's exchange buffer: inbox[2 (step parity)][world (sender)][gstride] words {float bits, step number}
     float *const *peers;
     int rank, world, gstride;
 };
 
-// one-shot cross-GPU exchange helpers (system-scope release / acquire on the flag words in peer memory)
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
     return v;
 }
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
@@ -241,8 +316,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// tagged words inside one GPU: {32 payload bits, step number}; a naturally aligned 64-bit access is single-copy atomic, so a
-// reader that sees this launch's step number also sees the payload - no fence, no barrier between producer and consumer
+__device__ __forceinline__ void red_release_gpu_add(unsigned int *p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// tagged words inside one GPU: {32 payload bits, launch number}; a naturally aligned 64-bit access is single-copy atomic, so a
+// reader that sees this launch's number also sees the payload - no fence, no barrier between producer and consumer
 __device__ __forceinline__ void st_tag(unsigned long long *p, unsigned int payload, unsigned int epoch) {
     const unsigned long long v = ((unsigned long long)epoch << 32) | payload;
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -257,49 +340,53 @@ __device__ __forceinline__ void st_tag_double(unsigned long long *p2, double x, 
     st_tag(p2, (unsigned int)(b >> 32), epoch);
     st_tag(p2 + 1, (unsigned int)b, epoch);
 }
-// polls until both halves carry `epoch` (bounded); ok is cleared on a time-out
-__device__ __forceinline__ double ld_tag_double(const unsigned long long *p2, unsigned int epoch, bool &ok) {
-    unsigned long long hi = 0, lo = 0;
-    bool got = false;
-    for (int it = 0; it < (1 << 22) && !got; ++it) {
-        hi = ld_tag(p2); lo = ld_tag(p2 + 1);
-        got = (unsigned int)(hi >> 32) == epoch && (unsigned int)(lo >> 32) == epoch;
+constexpr int TC_MAX_GRID = 160;   // lanes x 5: a warp holds one word per CTA in flight
+// one thread: wait until *count == nb, then acquire (the partial rows behind the counter).  false on time-out.
+__device__ __forceinline__ bool wait_count(const unsigned int *count, unsigned int nb, unsigned long long timeout_ns) {
+    const unsigned long long t0 = globaltimer_ns();
+    bool ok = true;
+    for (int it = 0; ld_relaxed_gpu(count) != nb; ++it)
+        if ((it & 63) == 63 && globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+    __threadfence();
+    return ok;
+}
+// one thread: poll a tagged word until it carries this launch's number; returns the payload
+__device__ __forceinline__ unsigned int wait_tag(const unsigned long long *p, unsigned int epoch, unsigned long long timeout_ns, bool &ok) {
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned long long v = ld_tag(p);
+    for (int it = 0; (unsigned int)(v >> 32) != epoch; ++it) {
+        if ((it & 63) == 63 && globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+        v = ld_tag(p);
     }
-    ok = ok && got;
-    return __longlong_as_double((long long)(((hi & 0xffffffffull) << 32) | (lo & 0xffffffffull)));
+    return (unsigned int)v;
 }
-__device__ __forceinline__ float ld_relaxed_sys(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// grid-wide barrier for a grid whose CTAs are all resident (cooperative launch): bounded spin, false on time-out.
-// bar = {arrival count, generation}, both zero once (workspace allocation); the last CTA to arrive resets the count and
-// advances the generation, so the same pair serves every barrier of every launch with no host-side reset in between.
-__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nblocks) {
-    __syncthreads();
-    __shared__ int ok_s;
-    if (threadIdx.x == 0) {
-        unsigned int gen, cur;
-        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");   // cannot advance before this CTA arrives
-        __threadfence();
-        int ok = 1;
-        if (atomicAdd(bar, 1u) == nblocks - 1) {
-            atomicExch(bar, 0u);
-            __threadfence();
-            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
-        } else {
-            ok = 0;
-            for (int it = 0; it < (1 << 24); ++it) {
-                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(cur) : "l"(bar + 1) : "memory");
-                if (cur != gen) { ok = 1; break; }
-            }
+// one warp: sum over the CTAs of a tagged double (lane l adds CTAs l, l + 32, ... in ascending order, then a fixed shuffle
+// tree: bit-reproducible); every word is polled until it carries this launch's number, all of a lane's words in flight
+__device__ __forceinline__ double sum_tagged_doubles(const unsigned long long *tagw, int nb, unsigned int epoch, int lane, unsigned long long timeout_ns,
+                                                     bool &ok) {
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned long long hi[TC_MAX_GRID / 32], lo[TC_MAX_GRID / 32];
+    bool all = false;
+    for (int it = 0; !all; ++it) {
+        bool mine = true;
+#pragma unroll
+        for (int k = 0; k < TC_MAX_GRID / 32; ++k) {
+            const int bl = lane + 32 * k;
+            hi[k] = lo[k] = (unsigned long long)epoch << 32;
+            if (bl < nb) { hi[k] = ld_tag(tagw + 2 * bl); lo[k] = ld_tag(tagw + 2 * bl + 1); }
+            mine = mine && (unsigned int)(hi[k] >> 32) == epoch && (unsigned int)(lo[k] >> 32) == epoch;
         }
-        ok_s = ok;
+        all = __all_sync(0xffffffffu, mine);
+        if (!all && (it & 63) == 63 && globaltimer_ns() - t0 > timeout_ns) break;
     }
-    __syncthreads();
-    return ok_s != 0;
+    ok = ok && all;
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < TC_MAX_GRID / 32; ++k)
+        if (lane + 32 * k < nb) a += __longlong_as_double((long long)(((hi[k] & 0xffffffffull) << 32) | (lo[k] & 0xffffffffull)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
 }
 
 // sum over the CTAs' partial rows of parameter i, slice sl of RED_SL (blocks sl, sl + RED_SL, ... in ascending order)
@@ -315,30 +402,6 @@ __device__ __forceinline__ float reduce_slice(const float *__restrict__ partials
         }
 #pragma unroll
         for (int u = 0; u < RED_MAX; ++u) s += v[u];
-    }
-    return s;
-}
-// the same over TAGGED partial rows (fused step): every word is polled until it carries this launch's step number, so the
-// reduction needs no grid barrier behind the producers; the summation order is the one above (bit-identical result)
-__device__ __forceinline__ float reduce_slice_tagged(const unsigned long long *__restrict__ partials, int nblocks, int stride, int i, int sl,
-                                                     unsigned int epoch, bool &ok) {
-    float s = 0.f;
-    for (int base = sl; base < nblocks; base += RED_SL * RED_MAX) {
-        unsigned long long v[RED_MAX];
-        bool all = false;
-        for (int it = 0; it < (1 << 22) && !all; ++it) {
-            if (it) __nanosleep(400);   // the poll of a whole grid is ~11 MB of L2 reads per round: leave the producers their bandwidth
-            all = true;
-#pragma unroll
-            for (int u = 0; u < RED_MAX; ++u) {
-                const int bl = base + u * RED_SL;
-                v[u] = bl < nblocks ? ld_tag(partials + (size_t)bl * stride + i) : ((unsigned long long)epoch << 32);
-                all = all && (unsigned int)(v[u] >> 32) == epoch;
-            }
-        }
-        ok = ok && all;
-#pragma unroll
-        for (int u = 0; u < RED_MAX; ++u) s += __uint_as_float((unsigned int)v[u]);
     }
     return s;
 }
@@ -366,68 +429,84 @@ __device__ __forceinline__ float reduce_tree(float (&t)[RED_SL]) {
 // optional phase timestamps of CTA 0 (PRL_TC_TIMING=1 in the environment prints them after the launch; debugging aid)
 __device__ long long g_tc_clock[32];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tc_clock[i] = clock64(); } while (0)
-// per-CTA wall-clock marks (ns): [cta][0] first instruction, [1] tiles done, [2] partials written, [3] last instruction
-__device__ unsigned long long g_tc_span[160 * 4 + 8];
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
-    return v;
-}
-#define TC_SPAN0(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tc_span[640 + (i)] = globaltimer_ns(); } while (0)
-#define TC_SPAN(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_tc_span[blockIdx.x * 4 + (i)] = globaltimer_ns(); } while (0)
+// per-CTA wall-clock marks (ns): [cta][0] first instruction, [1] tiles done, [2] partials written, [3] last instruction,
+// [4] READY flag raised, [5] all flags seen, [6] slices reduced, [7] norm known
+__device__ unsigned long long g_tc_span[160 * 8];
+#define TC_SPAN(i) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_tc_span[blockIdx.x * 8 + (i)] = globaltimer_ns(); } while (0)
 
 // ===================================================================================================== the kernel
-// NA = compile-time bound of the output widths (action_dim rounded up to 2, 4 or 8): the per-output loops unroll over it
-template <int NA>
+// NA = compile-time bound of the actor's output width (action_dim rounded up to 2, 4 or 8): the per-output loops unroll over
+// it.  XR = observation values kept in registers (4 or 8; observ_dim > XR reads the rest on demand).
+template <int NA, int XR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
               float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
               int *__restrict__ status, TcOptimizer opt, int qpc) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[6];          // MMA completion: actor forward, actor backward, critic dgrad, trunk wgrad, critic wgrad, critic forward
     __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
     __shared__ uint32_t tmem_slot;
-    __shared__ double red[32];
-    __shared__ float b2s[4][2][TC_MAX_A];
+    __shared__ double red[3][4];          // loss sums per row quarter
+    __shared__ float b2s[4][TC_MAX_A + 1];
+    __shared__ int tail_ok_s;
+    __shared__ float coef_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_mma_warp = warp == TC_COMPUTE / 32;
     const int rq = warp & 3, q = (warp >> 2) & 3;   // row quarter (= tensor-memory lane quarter), feature quarter
     const int r = rq * 32 + lane, j0 = TC_W * q;    // row of the tile, first feature of this thread
-    const int O = L.O, A = L.A;
+    const int O = L.O, A = L.A, nout0 = L.head[0].out;
     TC_STAMP(0);
     TC_SPAN(0);
+    if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);   // overlaps the parameter staging of the other warps
+
+    // ---- everything the launch needs from global memory besides the rows is requested up front (one exposed latency)
+    const bool fused = opt.params_rw != nullptr;
+    int64_t opt_step = 0;
+    double opt_p1 = 0.0, opt_p2 = 0.0;
+    unsigned int epoch = 0;
+    if (fused) {
+        // optimiser clock, read before anybody can advance it (CTA 0 does, at the very end); the launch number tags the
+        // READY flags and the squared-norm words of this launch (kept in the workspace header, advanced by CTA 0 at the end)
+        opt_step = opt.clock[0];
+        opt_p1 = reinterpret_cast<const double *>(opt.clock)[1];
+        opt_p2 = reinterpret_cast<const double *>(opt.clock)[2];
+        epoch = __ldcg(reinterpret_cast<const unsigned int *>(status) + 3) + 1u;
+    }
 
     // ---- carve shared memory (all pointers derive from smem_raw so they stay in the shared state space)
     unsigned char *sW = smem_raw, *sF = sW + 3 * PIECE, *sDZ = sF + 3 * PIECE, *sX = sDZ + 4 * PIECE;
     float *sSmall = reinterpret_cast<float *>(sX + 3 * XPIECE);
     float *s_w0t = sSmall, *s_g0w = s_w0t + O * HID, *s_g0b = s_g0w + HID;
     float *s_head0 = s_g0b + HID;                                   // per head: gw[64] gb[64] w2[out][64] b2[round4(out)]
-    const int head0_floats = 2 * HID + L.head[0].out * HID + round4(L.head[0].out);
+    const int head0_floats = 2 * HID + nout0 * HID + round4(nout0);
     float *s_head1 = s_head0 + head0_floats;
-    float *s_po = s_head1 + 2 * HID + L.head[1].out * HID + round4(L.head[1].out);   // [4 q][128 r][NA] partial head outputs
-    float *s_red = s_po + 4 * TC_ROWS * NA;                                            // [4 rq][NQ][64] final combine
+    float *s_po0 = sSmall + ((tc_small_floats(L) + 3) & ~3);        // [4 q][128 r][NA] partial actor outputs
+    float *s_po1 = s_po0 + 4 * TC_ROWS * NA;                        // [4 q][128 r]     partial critic outputs
 
     // ---- stage parameters: fp32 small ones; W1 of both heads as bf16x3 in the operand layout (row n = h*64 + j).
-    // Every global load is issued before the first dependent shared-memory store (one exposed memory latency, not ten).
+    // The two hidden-layer matrices and W0 are staged CENTRED over each GroupNorm group of output features (see the header).
     {
-        float v[TC_W];
-        const int n_small0 = HID * O, n_small1 = n_small0 + 2 * HID, n_h0 = 2 * HID + L.head[0].out * HID + L.head[0].out,
+        f2 v[8];
+        const int n_small0 = HID * O, n_small1 = n_small0 + 2 * HID, n_h0 = 2 * HID + nout0 * HID + nout0,
                   n_h1 = 2 * HID + L.head[1].out * HID + L.head[1].out, n_small = n_small1 + n_h0 + n_h1;
         if (!is_mma_warp) {
             // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
-            const float4 *wrow = reinterpret_cast<const float4 *>(params + L.head[r >> 6].w1 + (r & 63) * HID + j0);
-            if ((L.head[r >> 6].w1 & 3) == 0) {   // warp-uniform (a warp's rows belong to one head)
+            const int w1off = (r >> 6) ? L.head[1].w1 : L.head[0].w1;   // (no dynamic index into the kernel-parameter struct)
+            const float *wrow = params + w1off + (r & 63) * HID + j0;
+            TC_STAMP(19);
+            if ((w1off & 3) == 0) {   // warp-uniform (a warp's rows belong to one head)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { const float4 t = __ldg(wrow + k); v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+                for (int k = 0; k < 4; ++k) { const float4 t = __ldg(reinterpret_cast<const float4 *>(wrow) + k); v[2 * k] = mk2(t.x, t.y); v[2 * k + 1] = mk2(t.z, t.w); }
             } else {
-                const float *ws = reinterpret_cast<const float *>(wrow);
 #pragma unroll
-                for (int k = 0; k < TC_W; ++k) v[k] = __ldg(ws + k);
+                for (int k = 0; k < 8; ++k) v[k] = mk2(__ldg(wrow + 2 * k), __ldg(wrow + 2 * k + 1));
             }
         }
-        // small parameters: w0 (stored transposed), then three blocks that are contiguous both in `params` and in shared
-        // memory: {g0w, g0b}, head 0 {gw, gb, w2, b2}, head 1 {gw, gb, w2, b2}
+        if (blockIdx.x == 0 && tid == 0 && v[0].x == 123456.789f) g_tc_clock[31] = 1;   // (timing aid: waits for the W1 row)
+        TC_STAMP(20);
+        // small parameters: w0 (stored transposed and centred), then three blocks that are contiguous both in `params` and in
+        // shared memory: {g0w, g0b}, head 0 {gw, gb, w2, b2}, head 1 {gw, gb, w2, b2}
         for (int base = 0; base < n_small; base += 2 * TC_THREADS) {
             float sv[2];
             float *dst[2];
@@ -435,7 +514,15 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int u = 0; u < 2; ++u) {
                 const int i = base + u * TC_THREADS + tid;
                 dst[u] = nullptr;
-                if (i < n_small0) { const int j = i / O, o = i - j * O; dst[u] = s_w0t + o * HID + j; sv[u] = __ldg(params + L.w0 + i); }
+                if (i < n_small0) {
+                    const int j = i / O, o = i - j * O;
+                    const float *gp = params + L.w0 + (j & ~(GSIZE - 1)) * O + o;   // the 8 rows of j's group, column o
+                    float m = 0.f;
+#pragma unroll
+                    for (int t = 0; t < GSIZE; ++t) m += __ldg(gp + t * O);
+                    dst[u] = s_w0t + o * HID + j;
+                    sv[u] = __ldg(params + L.w0 + i) - m * (1.0f / GSIZE);
+                }
                 else if (i < n_small1) { dst[u] = s_g0w + (i - n_small0); sv[u] = __ldg(params + L.g0w + (i - n_small0)); }
                 else if (i < n_small1 + n_h0) { dst[u] = s_head0 + (i - n_small1); sv[u] = __ldg(params + L.head[0].gw + (i - n_small1)); }
                 else if (i < n_small) { dst[u] = s_head1 + (i - n_small1 - n_h0); sv[u] = __ldg(params + L.head[1].gw + (i - n_small1 - n_h0)); }
@@ -444,7 +531,16 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int u = 0; u < 2; ++u)
                 if (dst[u]) *dst[u] = sv[u];
         }
+        TC_STAMP(17);
         if (!is_mma_warp) {
+            // centre W1 over the 8 rows of the GroupNorm group: lanes 8i..8i+7 of a warp hold rows 8i..8i+7 of one head
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                f2 s = v[k];
+#pragma unroll
+                for (int o = 1; o < GSIZE; o <<= 1) { s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o); }
+                v[k] = fma2(s, dup2(-1.0f / GSIZE), v[k]);
+            }
             store_pieces16(sW, r, q, v);
             // zero slot behind the three DZ pieces; X pieces (columns >= O stay zero for the whole kernel)
 #pragma unroll
@@ -457,8 +553,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         for (int i = 0; i < 4; ++i) mbar_init(&sbar[i], TC_COMPUTE);
         for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
+        tail_ok_s = 1;
     }
-    if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);
+    TC_STAMP(18);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -480,30 +577,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const int myq = (int)max((int64_t)0, min((int64_t)qpc, (b + 31) / 32 - (int64_t)blockIdx.x * qpc));
     const int ntiles = (myq + 3) >> 2;
     uint32_t it = 0;
-    double l_pol = 0.0, l_val = 0.0, l_ent = 0.0;
     const int P = L.total;
     float *part = partials + (size_t)blockIdx.x * part_stride;
-    // fused optimiser step: this CTA's partial row is written as tagged 64-bit words (see st_tag)
-    const bool fused = opt.params_rw != nullptr;
-    unsigned long long *part64 = reinterpret_cast<unsigned long long *>(partials) + (size_t)blockIdx.x * part_stride;
-    // optimiser clock, read before anybody can advance it (CTA 0 does, after the second grid barrier)
-    int64_t opt_step = 0;
-    double opt_p1 = 0.0, opt_p2 = 0.0;
-    if (opt.params_rw) {
-        opt_step = opt.clock[0] + 1;
-        const double *pw = reinterpret_cast<const double *>(opt.clock) + 1;
-        const bool have = opt_step > 1 && pw[0] > 0.0;
-        opt_p1 = have ? pw[0] * 0.9 : pow(0.9, (double)opt_step);
-        opt_p2 = have ? pw[1] * 0.999 : pow(0.999, (double)opt_step);
-    }
-    // the tag of every word this launch publishes inside the GPU: a launch counter kept in the workspace header (word 3),
-    // read by everybody here and advanced by CTA 0 at the very end - monotonic per workspace, whatever optimiser uses it
-    const unsigned int epoch = fused ? __ldcg(reinterpret_cast<const unsigned int *>(status) + 3) + 1u : 0u;
-    // one partial-gradient entry: plain float (separate reduction kernel) or tagged word (fused step)
-    auto put = [&](int idx, float v) {
-        if (fused) st_tag(part64 + idx, __float_as_uint(v), epoch);
-        else part[idx] = v;
-    };
 
     if (is_mma_warp) {
         // =============================================================================== MMA-issue warp
@@ -529,17 +604,15 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         }
     } else {
         // =============================================================================== compute warps
-        // column-sum accumulators live in shared memory: s_red[rq][quantity][64 features]; this warp owns features j0..j0+15
-        // of row quarter rq.  Quantities: 0 dgamma0, 1 dbeta0, then per head: dgamma, dbeta, dW2[a] (a < out).
-        const int NQ = tc_num_q(L);
-        float *acc = s_red + (size_t)rq * NQ * HID + j0;
-        const int qh[2] = {2, 2 + 2 + L.head[0].out};
-        for (int i = lane; i < NQ * TC_W; i += 32) acc[(i / TC_W) * HID + (i % TC_W)] = 0.f;
-        if (q == 0 && lane < 2 * TC_MAX_A) (&b2s[rq][0][0])[lane] = 0.f;
-        __syncwarp();
+        // column-sum accumulators: registers, live across all tiles (.x: feature f(lane) of this thread's group 0, .y: of group 1)
+        f2 acc_g0 = dup2(0.f), acc_b0 = dup2(0.f), acc_gh[2] = {dup2(0.f), dup2(0.f)}, acc_bh[2] = {dup2(0.f), dup2(0.f)}, acc_w2c = dup2(0.f);
+        f2 acc_w2a[NA];
+        float b2a[NA], b2c = 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) { acc_w2a[a] = dup2(0.f); b2a[a] = 0.f; }
+        float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
 
         // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
-        constexpr int XR = 8;   // observation values kept in registers (observ_dim > 8 reads the rest on demand)
         float xn[XR];
         {
             const int64_t row0 = row_base + r;
@@ -562,9 +635,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 if (q == 0)
                     for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4 *>(sX + c * CHUNK + r * 16) = make_uint4(0, 0, 0, 0);
                 staged(&sbar[0]);
-                bar_compute();       // the live warps' partial-output exchange, actor
                 staged(&sbar[1]);
-                bar_compute();       // critic
                 staged(&sbar[2]);
                 staged(&sbar[3]);
                 continue;
@@ -585,58 +656,66 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             const float ret_i = live ? __ldg(returns + row) : 0.f;
             const int act = live ? (int)__ldg(actions + row) : 0;
 
-            // ================= trunk forward (CUDA cores): z0 = W0 x, GroupNorm, SiLU -> F pieces, X pieces
-            auto trunk_pre = [&](float (&zh0)[TC_W], float (&rs0)[2]) {
+            // ================= trunk forward (CUDA cores): z0 = W0c x, GroupNorm, SiLU -> F pieces, X pieces; zhat0 and SiLU'
+            // are parked in tensor memory for the trunk backward
+            float rs0[2];
+            {
+                f2 z[8];
 #pragma unroll
-                for (int j = 0; j < TC_W; ++j) zh0[j] = 0.f;
+                for (int k = 0; k < 8; ++k) z[k] = dup2(0.f);
 #pragma unroll
                 for (int i = 0; i < XR; ++i) {
                     if (i < O) {
-                        float w[TC_W];
+                        f2 w[8];
                         load16(s_w0t + i * HID + j0, w);
 #pragma unroll
-                        for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(x[i], w[j], zh0[j]);
+                        for (int k = 0; k < 8; ++k) z[k] = fma2(dup2(x[i]), w[k], z[k]);
                     }
                 }
                 for (int i = XR; i < O; ++i) {
                     const float xi = xmask * __ldg(xrow + i);
-                    float w[TC_W];
+                    f2 w[8];
                     load16(s_w0t + i * HID + j0, w);
 #pragma unroll
-                    for (int j = 0; j < TC_W; ++j) zh0[j] = fmaf(xi, w[j], zh0[j]);
+                    for (int k = 0; k < 8; ++k) z[k] = fma2(dup2(xi), w[k], z[k]);
                 }
-                gn_normalize16(zh0, rs0);
-            };
-            {
-                float zh0[TC_W], rs0[2];
-                trunk_pre(zh0, rs0);
-                float f[TC_W], g0w[TC_W], g0b[TC_W];
-                load16(s_g0w + j0, g0w);
-                load16(s_g0b + j0, g0b);
+                gn_normalize_centred(z, rs0);
+                f2 f[8], d0[8];
 #pragma unroll
-                for (int j = 0; j < TC_W; ++j) {
-                    const float y = fmaf(zh0[j], g0w[j], g0b[j]);
-                    f[j] = y * fast_sigmoid(y);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 g = *reinterpret_cast<const float4 *>(s_g0w + j0 + 4 * k4), bt = *reinterpret_cast<const float4 *>(s_g0b + j0 + 4 * k4);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int k = 2 * k4 + hf;
+                        const f2 y = fma2(z[k], hf ? mk2(g.z, g.w) : mk2(g.x, g.y), hf ? mk2(bt.z, bt.w) : mk2(bt.x, bt.y));
+                        const f2 s = sigmoid2(y);
+                        f[k] = mul2(y, s);
+                        d0[k] = fma2(f[k], fma2(s, dup2(-1.0f), dup2(1.0f)), s);   // SiLU'(y) = s + y s (1 - s)
+                    }
                 }
+                tmem_st16_f2(lane_base + TM_ZH0 + j0, z);
+                tmem_st16_f2(lane_base + TM_DS0 + j0, d0);
                 // the previous tile's trunk-wgrad MMAs read X and DZ; its head MMAs (already waited for) read F
                 if (it > 0) mma_ok &= mbar_wait(&bars[3], parity ^ 1);
                 store_pieces16(sF, r, q, f);
                 if (q == 0) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        uint32_t q0[4], q1[4], q2[4];
+                        if (8 * c < O) {   // (columns >= O stay zero from the set-up)
+                            uint32_t q0[4], q1[4], q2[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = 8 * c + 2 * i;
-                            float xa, xb;
-                            if (c == 0) { xa = x[e & 7]; xb = x[(e + 1) & 7]; }
-                            else { xa = e < O ? xmask * __ldg(xrow + e) : 0.f; xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f; }
-                            split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
+                            for (int i = 0; i < 4; ++i) {
+                                const int e = 8 * c + 2 * i;
+                                float xa, xb;
+                                if (e + 1 < XR) { xa = x[e < XR ? e : 0]; xb = x[e + 1 < XR ? e + 1 : 0]; }
+                                else { xa = e < O ? xmask * __ldg(xrow + e) : 0.f; xb = e + 1 < O ? xmask * __ldg(xrow + e + 1) : 0.f; }
+                                split_bf16x3(xa, xb, q0[i], q1[i], q2[i]);
+                            }
+                            unsigned char *p = sX + c * CHUNK + r * 16;
+                            *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+                            *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+                            *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
                         }
-                        unsigned char *p = sX + c * CHUNK + r * 16;
-                        *reinterpret_cast<uint4 *>(p) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
-                        *reinterpret_cast<uint4 *>(p + XPIECE) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-                        *reinterpret_cast<uint4 *>(p + 2 * XPIECE) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
                     }
                 }
             }
@@ -647,67 +726,84 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             if (it == 0) TC_STAMP(4);
 
             // ================= heads: forward epilogue, loss, backward epilogue -> DZ pieces, tensor-core dgrad + wgrad
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int nout = L.head[h].out;
-                const float *sh = h ? s_head1 : s_head0;
+            auto head = [&](auto HC) {
+                constexpr int H = decltype(HC)::value;
+                constexpr int NO = H == 0 ? NA : 1;             // compile-time bound of this head's output width
+                const int nout = H == 0 ? nout0 : 1;
+                const float *sh = H ? s_head1 : s_head0;
                 const float *w2 = sh + 2 * HID;
-                float gw[TC_W], gb[TC_W];
-                load16(sh + j0, gw);
-                load16(sh + HID + j0, gb);
-                float zhat[TC_W], rstd[2], sg[TC_W];
-                if (h == 1) { mma_ok &= mbar_wait(&bars[5], parity); fence_after_sync(); }   // critic forward complete
-                tmem_ld16w(lane_base + TM_Z + 64 * h + j0, zhat);
-                gn_normalize16(zhat, rstd);
-                float po[NA];
+                float *spo = H ? s_po1 : s_po0;
+                if (H == 1) { mma_ok &= mbar_wait(&bars[5], parity); fence_after_sync(); }   // critic forward complete
+                f2 zh[8], ds[8];
+                float rstd[2];
+                tmem_ld16_f2(lane_base + TM_Z + 64 * H + j0, zh);
+                gn_normalize_centred(zh, rstd);
+                {
+                    f2 hj[8], po2[NO];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) po[a] = 0.f;
+                    for (int a = 0; a < NO; ++a) po2[a] = dup2(0.f);
 #pragma unroll
-                for (int j = 0; j < TC_W; ++j) {
-                    const float y = fmaf(zhat[j], gw[j], gb[j]);
-                    sg[j] = fast_sigmoid(y);
-                    const float hj = y * sg[j];
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 g = *reinterpret_cast<const float4 *>(sh + j0 + 4 * k4), bt = *reinterpret_cast<const float4 *>(sh + HID + j0 + 4 * k4);
 #pragma unroll
-                    for (int a = 0; a < NA; ++a)
-                        if (a < nout) po[a] = fmaf(hj, w2[a * HID + j0 + j], po[a]);
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int k = 2 * k4 + hf;
+                            const f2 y = fma2(zh[k], hf ? mk2(g.z, g.w) : mk2(g.x, g.y), hf ? mk2(bt.z, bt.w) : mk2(bt.x, bt.y));
+                            const f2 s = sigmoid2(y);
+                            hj[k] = mul2(y, s);
+                            ds[k] = fma2(hj[k], fma2(s, dup2(-1.0f), dup2(1.0f)), s);
+                        }
+#pragma unroll
+                        for (int a = 0; a < NO; ++a) {
+                            if (a < nout) {
+                                const float4 w = *reinterpret_cast<const float4 *>(w2 + a * HID + j0 + 4 * k4);
+                                po2[a] = fma2(hj[2 * k4], mk2(w.x, w.y), po2[a]);
+                                po2[a] = fma2(hj[2 * k4 + 1], mk2(w.z, w.w), po2[a]);
+                            }
+                        }
+                    }
+                    tmem_st16_f2(lane_base + TM_HJ + j0, hj);   // parked for dW2
+#pragma unroll
+                    for (int a = 0; a < NO; ++a)
+                        if (a < nout) spo[(q * TC_ROWS + r) * NO + a] = po2[a].x + po2[a].y;
                 }
+                bar_quarter(rq);   // the four threads of a row have published their partial outputs
+                float out[NO];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) s_po[(q * TC_ROWS + r) * NA + a] = po[a];
-                bar_compute();
-                float out[NA];
-#pragma unroll
-                for (int a = 0; a < NA; ++a)
-                    out[a] = (a < nout) ? w2[nout * HID + a] + ((s_po[(0 * TC_ROWS + r) * NA + a] + s_po[(1 * TC_ROWS + r) * NA + a]) +
-                                                              (s_po[(2 * TC_ROWS + r) * NA + a] + s_po[(3 * TC_ROWS + r) * NA + a]))
+                for (int a = 0; a < NO; ++a)
+                    out[a] = (a < nout) ? w2[nout * HID + a] + ((spo[(0 * TC_ROWS + r) * NO + a] + spo[(1 * TC_ROWS + r) * NO + a]) +
+                                                              (spo[(2 * TC_ROWS + r) * NO + a] + spo[(3 * TC_ROWS + r) * NO + a]))
                                         : 0.f;
                 // ---- loss and output gradients (the four threads of a row compute them redundantly; q == 0 keeps the sums)
-                float dout[NA];
+                float dout[NO];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) dout[a] = 0.f;
-                if (h == 0) {
+                for (int a = 0; a < NO; ++a) dout[a] = 0.f;
+                if (H == 0) {
                     if (live) {
                         float m = out[0];
 #pragma unroll
-                        for (int a = 1; a < NA; ++a)
+                        for (int a = 1; a < NO; ++a)
                             if (a < A) m = fmaxf(m, out[a]);
-                        float p[NA], Ssum = 0.f, Psum = 0.f;
+                        float p[NO], Ssum = 0.f, Psum = 0.f;
 #pragma unroll
-                        for (int a = 0; a < NA; ++a) { p[a] = (a < A) ? expf(out[a] - m) : 0.f; Ssum += p[a]; }
+                        for (int a = 0; a < NO; ++a) { p[a] = (a < A) ? fast_exp(out[a] - m) : 0.f; Ssum += p[a]; }
+                        const float iS = rcp_approx(Ssum);
 #pragma unroll
-                        for (int a = 0; a < NA; ++a) { p[a] = p[a] / Ssum; Psum += p[a]; }
+                        for (int a = 0; a < NO; ++a) { p[a] *= iS; Psum += p[a]; }
+                        const float iP = rcp_approx(Psum);
                         float pa = 0.f, ent = 0.f;
 #pragma unroll
-                        for (int a = 0; a < NA; ++a) {
+                        for (int a = 0; a < NO; ++a) {
                             if (a < A) {
-                                p[a] = p[a] / Psum;
-                                const float l = logf(fminf(fmaxf(p[a], F32_EPS), 1.0f - F32_EPS));
-                                ent -= l * p[a];
+                                p[a] *= iP;
+                                const float l = fast_log(fminf(fmaxf(p[a], F32_EPS), 1.0f - F32_EPS));
+                                ent = fmaf(-l, p[a], ent);
                                 if (a == act) pa = p[a];
                             }
                         }
-                        const float logp = logf(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
+                        const float logp = fast_log(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
                         const float dl = logp - old_i;
-                        const float rr = expf(fminf(fmaxf(dl, -20.f), 20.f));
+                        const float rr = fast_exp(fminf(fmaxf(dl, -20.f), 20.f));
                         const float s1 = rr * adv_i;
                         const float s2 = fminf(fmaxf(rr, 1.0f - clip), 1.0f + clip) * adv_i;
                         const float g1 = s1 < s2 ? 1.f : (s1 > s2 ? 0.f : 0.5f);   // torch.min splits ties evenly
@@ -716,7 +812,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                         float dlogp = -inv_count * adv_i * (g1 + (1.f - g1) * in_clip) * rr * in20;
                         if (!(pa >= F32_EPS && pa <= 1.0f - F32_EPS)) dlogp = 0.f;   // clamp in probs_to_logits blocks the gradient
 #pragma unroll
-                        for (int a = 0; a < NA; ++a)
+                        for (int a = 0; a < NO; ++a)
                             if (a < A) dout[a] = dlogp * ((a == act ? 1.f : 0.f) - p[a]);
                         if (q == 0) { l_pol += -fminf(s1, s2); l_ent += ent; }
                     }
@@ -725,73 +821,88 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     if (q == 0) l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
                     dout[0] = 0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f));
                 }
+                // ---- dy = (dout . W2) * SiLU'(y), in place of ds
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    f2 dh0 = dup2(0.f), dh1 = dup2(0.f);
+#pragma unroll
+                    for (int a = 0; a < NO; ++a) {
+                        if (a < nout) {
+                            const float4 w = *reinterpret_cast<const float4 *>(w2 + a * HID + j0 + 4 * k4);
+                            dh0 = fma2(dup2(dout[a]), mk2(w.x, w.y), dh0);
+                            dh1 = fma2(dup2(dout[a]), mk2(w.z, w.w), dh1);
+                        }
+                    }
+                    ds[2 * k4] = mul2(dh0, ds[2 * k4]);
+                    ds[2 * k4 + 1] = mul2(dh1, ds[2 * k4 + 1]);
+                }
+                // ---- GroupNorm backward -> dz, handed to the tensor core BEFORE the column sums below: the dgrad / wgrad MMAs
+                // run under them (what the trunk backward waits for is the critic's dgrad)
+                {
+                    f2 dz[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dz[k] = ds[k];
+                    gn_backward16(dz, zh, rstd, sh + j0);
+                    if (it == 0) TC_STAMP(5 + 3 * H);
+                    // the actor's MMAs read DZ: they must have completed before the critic overwrites it
+                    if (H == 1) mma_ok &= mbar_wait(&bars[1], parity);
+                    store_pieces16(sDZ, r, q, dz);
+                    staged(&sbar[1 + H]);
+                    if (it == 0) TC_STAMP(6 + 3 * H);
+                }
                 // ---- output-layer gradients: dW2[a][j] = sum_r dout[a] h_j, db2[a] = sum_r dout[a]
+                {
+                    f2 hj[8];
+                    tmem_ld16_f2(lane_base + TM_HJ + j0, hj);
 #pragma unroll
-                for (int a = 0; a < NA; ++a) {
-                    if (a < nout) {
-                        float t[TC_W];
+                    for (int a = 0; a < NO; ++a) {
+                        if (a < nout) {
+                            f2 t[8];
 #pragma unroll
-                        for (int j = 0; j < TC_W; ++j) t[j] = dout[a] * (fmaf(zhat[j], gw[j], gb[j]) * sg[j]);
-                        colsum16(t, acc + (qh[h] + 2 + a) * HID);
-                        if (q == 0) {
-                            const float sb = warp_sum(dout[a]);
-                            if (lane == 0) b2s[rq][h][a] += sb;
+                            for (int k = 0; k < 8; ++k) t[k] = mul2(hj[k], dup2(dout[a]));
+                            if (H == 0) { colsum16(t, acc_w2a[a]); b2a[a] += dout[a]; }
+                            else { colsum16(t, acc_w2c); b2c += dout[a]; }
                         }
                     }
                 }
-                // ---- dy (in place of sg), GroupNorm-affine gradients, GroupNorm backward -> dz
-#pragma unroll
-                for (int j = 0; j < TC_W; ++j) {
-                    float dh = 0.f;
-#pragma unroll
-                    for (int a = 0; a < NA; ++a)
-                        if (a < nout) dh = fmaf(dout[a], w2[a * HID + j0 + j], dh);
-                    const float y = fmaf(zhat[j], gw[j], gb[j]);
-                    sg[j] = dh * sg[j] * fmaf(y, 1.0f - sg[j], 1.0f);
-                }
+                // ---- GroupNorm-affine gradients
                 {
-                    float t[TC_W];
+                    f2 t[8];
 #pragma unroll
-                    for (int j = 0; j < TC_W; ++j) t[j] = sg[j] * zhat[j];
-                    colsum16(t, acc + qh[h] * HID);
-                    colsum16(sg, acc + (qh[h] + 1) * HID);
+                    for (int k = 0; k < 8; ++k) t[k] = mul2(ds[k], zh[k]);
+                    colsum16(t, acc_gh[H]);
+                    colsum16(ds, acc_bh[H]);
                 }
-                gn_backward16(sg, zhat, rstd, gw);   // sg now holds dz
-                if (it == 0) TC_STAMP(5 + 3 * h);
-                // the actor's MMAs read DZ: they must have completed before the critic overwrites it
-                if (h == 1) mma_ok &= mbar_wait(&bars[1], parity);
-                store_pieces16(sDZ, r, q, sg);
-                staged(&sbar[1 + h]);
-                if (it == 0) TC_STAMP(6 + 3 * h);
-            }
+            };
+            head(std::integral_constant<int, 0>{});
+            head(std::integral_constant<int, 1>{});
 
             // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
             {
-                float df[TC_W], g0w[TC_W], g0b[TC_W], zh0[TC_W], rs0[2];
-                trunk_pre(zh0, rs0);   // recomputed (cheap) rather than kept in registers across the head phases
-                load16(s_g0w + j0, g0w);
-                load16(s_g0b + j0, g0b);
+                f2 df[8], zh0[8], d0[8];
+                tmem_ld16x2_f2(lane_base + TM_ZH0 + j0, zh0, lane_base + TM_DS0 + j0, d0);
                 mma_ok &= mbar_wait(&bars[2], parity);    // critic dgrad complete -> DF final
                 fence_after_sync();
                 if (it == 0) TC_STAMP(11);
-                tmem_ld16w(lane_base + TM_DF + j0, df);
+                tmem_ld16_f2(lane_base + TM_DF + j0, df);
 #pragma unroll
-                for (int j = 0; j < TC_W; ++j) {
-                    const float y = fmaf(zh0[j], g0w[j], g0b[j]);
-                    const float s = fast_sigmoid(y);
-                    df[j] = df[j] * s * fmaf(y, 1.0f - s, 1.0f);
-                }
+                for (int k = 0; k < 8; ++k) df[k] = mul2(df[k], d0[k]);
                 {
-                    float t[TC_W];
+                    f2 dz[8];
 #pragma unroll
-                    for (int j = 0; j < TC_W; ++j) t[j] = df[j] * zh0[j];
-                    colsum16(t, acc);
-                    colsum16(df, acc + HID);
+                    for (int k = 0; k < 8; ++k) dz[k] = df[k];
+                    gn_backward16(dz, zh0, rs0, s_g0w + j0);
+                    mma_ok &= mbar_wait(&bars[4], parity);    // critic wgrad complete -> DZ free again
+                    store_pieces16(sDZ, r, q, dz);
+                    staged(&sbar[3]);
                 }
-                gn_backward16(df, zh0, rs0, g0w);
-                mma_ok &= mbar_wait(&bars[4], parity);    // critic wgrad complete -> DZ free again
-                store_pieces16(sDZ, r, q, df);
-                staged(&sbar[3]);
+                {   // column sums under the trunk-wgrad MMAs
+                    f2 t[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t[k] = mul2(df[k], zh0[k]);
+                    colsum16(t, acc_g0);
+                    colsum16(df, acc_b0);
+                }
                 if (it == 0) TC_STAMP(12);
             }
         }
@@ -809,6 +920,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         float *scratch0 = reinterpret_cast<float *>(sF);              // [128][68] fp32 = 34 KB inside the 48 KB F region
         float *scratch1 = reinterpret_cast<float *>(sDZ);             // same, inside the 64 KB DZ region
         float *scratch2 = scratch1 + TC_ROWS * SS;                    // [128][17] for DW0
+        float *s_red = reinterpret_cast<float *>(sW);                 // [4 rq][NQ][64] column sums (the W region is free: every MMA has completed)
+        const int NQ = tc_num_q(L);
         {
             float v0[TC_W], v1[TC_W], v2[TC_W];
             tmem_ld16(lane_base + TM_DW + j0, v0);
@@ -824,72 +937,92 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 #pragma unroll
                 for (int i = 0; i < TC_W; ++i) scratch2[r * 17 + i] = v2[i];
             }
-            bar_compute();
-            for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
-                const int j = idx >> 6, k = idx & 63;
-                put(L.head[0].w1 + idx, (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f);
-                put(L.head[1].w1 + idx, (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f);
-            }
-            for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
-                const int j = idx / O, i = idx - j * O;
-                put(L.w0 + idx, (it > 0) ? scratch2[j * 17 + i] + scratch2[(64 + j) * 17 + i] : 0.f);
-            }
         }
-        // column-sum accumulators (already in s_red / b2s): combine the four row quarters
-        {
-            bar_compute();
-            for (int idx = tid; idx < NQ * HID; idx += TC_COMPUTE) {
-                const int qq = idx / HID, j = idx - qq * HID;
-                const float sm = (s_red[(0 * NQ + qq) * HID + j] + s_red[(1 * NQ + qq) * HID + j]) + (s_red[(2 * NQ + qq) * HID + j] + s_red[(3 * NQ + qq) * HID + j]);
-                int off;
-                if (qq == 0) off = L.g0w;
-                else if (qq == 1) off = L.g0b;
-                else {
-                    int k = qq - 2, h = 0;
-                    if (k >= 2 + L.head[0].out) { k -= 2 + L.head[0].out; h = 1; }
-                    off = (k == 0) ? L.head[h].gw : (k == 1) ? L.head[h].gb : L.head[h].w2 + (k - 2) * HID;
-                }
-                put(off + j, sm);
+        // column sums: one of the four lanes holding feature f of a group reports it; quantities: 0 dgamma0, 1 dbeta0, then per
+        // head: dgamma, dbeta, dW2[a] (a < out)
+        if ((lane & 3) == 0) {
+            const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            float *dst = s_red + (size_t)rq * NQ * HID + j0 + f;
+            auto rep = [&](int qi, f2 a) { dst[qi * HID] = a.x; dst[qi * HID + 8] = a.y; };
+            rep(0, acc_g0); rep(1, acc_b0);
+            rep(2, acc_gh[0]); rep(3, acc_bh[0]);
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                if (a < nout0) rep(4 + a, acc_w2a[a]);
+            rep(4 + nout0, acc_gh[1]); rep(5 + nout0, acc_bh[1]); rep(6 + nout0, acc_w2c);
+        }
+        if (q == 0) {
+            // db2 and the loss sums of this row quarter (fixed shuffle tree)
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const float sb = warp_sum(b2a[a]);
+                if (lane == 0) b2s[rq][a] = sb;
             }
-            if (tid < 2 * NA) {
-                const int h = tid / NA, a = tid % NA;
-                if (a < L.head[h].out) put(L.head[h].b2 + a, (b2s[0][h][a] + b2s[1][h][a]) + (b2s[2][h][a] + b2s[3][h][a]));
+            const float sc = warp_sum(b2c);
+            const double sp = warp_sum((double)l_pol), sv = warp_sum((double)l_val), se = warp_sum((double)l_ent);
+            if (lane == 0) { b2s[rq][TC_MAX_A] = sc; red[0][rq] = sp; red[1][rq] = sv; red[2][rq] = se; }
+        }
+        bar_compute();
+        for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
+            const int j = idx >> 6, k = idx & 63;
+            part[L.head[0].w1 + idx] = (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f;
+            part[L.head[1].w1 + idx] = (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f;
+        }
+        for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
+            const int j = idx / O, i = idx - j * O;
+            part[L.w0 + idx] = (it > 0) ? scratch2[j * 17 + i] + scratch2[(64 + j) * 17 + i] : 0.f;
+        }
+        for (int idx = tid; idx < NQ * HID; idx += TC_COMPUTE) {
+            const int qq = idx / HID, j = idx - qq * HID;
+            const float sm = (s_red[(0 * NQ + qq) * HID + j] + s_red[(1 * NQ + qq) * HID + j]) + (s_red[(2 * NQ + qq) * HID + j] + s_red[(3 * NQ + qq) * HID + j]);
+            int off;
+            if (qq == 0) off = L.g0w;
+            else if (qq == 1) off = L.g0b;
+            else {
+                int k = qq - 2, h = 0;
+                if (k >= 2 + nout0) { k -= 2 + nout0; h = 1; }
+                const int hgw = h ? L.head[1].gw : L.head[0].gw, hgb = h ? L.head[1].gb : L.head[0].gb, hw2 = h ? L.head[1].w2 : L.head[0].w2;
+                off = (k == 0) ? hgw : (k == 1) ? hgb : hw2 + (k - 2) * HID;
             }
+            part[off + j] = sm;
+        }
+        if (tid < NA) {
+            if (tid < nout0) part[L.head[0].b2 + tid] = (b2s[0][tid] + b2s[1][tid]) + (b2s[2][tid] + b2s[3][tid]);
+        } else if (tid == NA) {
+            part[L.head[1].b2] = (b2s[0][TC_MAX_A] + b2s[1][TC_MAX_A]) + (b2s[2][TC_MAX_A] + b2s[3][TC_MAX_A]);
+        } else if (tid >= 32 && tid < 35) {
+            const int k = tid - 32;
+            loss_partials[blockIdx.x * 4 + k] = (red[k][0] + red[k][1]) + (red[k][2] + red[k][3]);
         }
         TC_STAMP(15);
     }
-    // everyone, the MMA warp included (block_sum synchronises the whole CTA)
-    const double bp = block_sum<double>(l_pol, red);
-    const double bv = block_sum<double>(l_val, red);
-    const double be = block_sum<double>(l_ent, red);
-    if (tid == 0) {
-        if (fused) {
-            st_tag_double(opt.tagw + blockIdx.x * 8 + 0, bp, epoch);
-            st_tag_double(opt.tagw + blockIdx.x * 8 + 2, bv, epoch);
-            st_tag_double(opt.tagw + blockIdx.x * 8 + 4, be, epoch);
-        } else {
-            loss_partials[blockIdx.x * 4 + 0] = bp;
-            loss_partials[blockIdx.x * 4 + 1] = bv;
-            loss_partials[blockIdx.x * 4 + 2] = be;
-            loss_partials[blockIdx.x * 4 + 3] = 0.0;
-        }
-    }
     if (!mma_ok && lane == 0) atomicExch(status, 1);
     fence_before_sync();
-    __syncthreads();
+    __syncthreads();   // every thread's partial-row stores happen before the READY flag below
     if (is_mma_warp) tmem_dealloc(D.tmem, TM_COLS);
     TC_STAMP(16);
     TC_SPAN(2);
-    TC_SPAN(3);
-    if (!opt.params_rw) return;
+    if (!fused) { TC_SPAN(3); return; }
 
     // ================= fused optimiser tail: reduce -> clip_grad_norm_ -> AdamW on this CTA's slices of the parameters.
-    // No grid barrier anywhere: every CTA published its partial row, loss sums and (below) squared norm as TAGGED words, and
-    // the consumers poll the words they need until they carry this launch's step number.  (All CTAs are co-resident -
-    // cooperative launch - so the polls terminate; they are bounded anyway: status 2.)
+    // No grid barrier anywhere: READY flags behind the partial rows, tagged words for the squared norm (all CTAs are
+    // co-resident - cooperative launch - so the waits terminate; they are bounded in wall-clock time anyway: status 2).
     const int nb = gridDim.x;
-    bool tags_ok = true;
-    TC_SPAN0(0);
+    const bool leader = blockIdx.x == (unsigned)nb - 1;
+    if (tid == 0) {
+        red_release_gpu_add(opt.count, 1u);
+        TC_SPAN(4);
+        if (!wait_count(opt.count, (unsigned)nb, opt.timeout_ns)) tail_ok_s = 0;
+    }
+    __syncthreads();
+    TC_SPAN(5);
+    bool tags_ok = tail_ok_s != 0;
+    {   // this step's bias-correction powers (kept off the critical path above)
+        const bool have = opt_step > 0 && opt_p1 > 0.0;
+        opt_step += 1;
+        opt_p1 = have ? opt_p1 * 0.9 : pow(0.9, (double)opt_step);
+        opt_p2 = have ? opt_p2 * 0.999 : pow(0.999, (double)opt_step);
+    }
     // The parameters are cut into slices of RC = 64 (142 slices for P = 9 027); CTA c owns slices c, c + nb, ...  The cut does
     // not depend on the grid, so ranks whose minibatches have different row counts (different grids) agree on it.
     constexpr int RC = 64;                                            // parameters per slice
@@ -898,31 +1031,16 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     double *sq = reinterpret_cast<double *>(smem_raw + 8192);         // [RC] squared gradients
     double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slices
     const bool sharded = opt.world > 1;
-    // losses of the whole launch (one warp of CTA 0; the other CTAs' loss partials were written before the first grid barrier)
-    if (blockIdx.x == 0 && is_mma_warp && opt.loss_out) {
-        // lane l adds blocks l, l + 32, ... in ascending order, then a fixed shuffle tree: bit-reproducible
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int bl = lane; bl < nb; bl += 32) {
-            a0 += ld_tag_double(opt.tagw + bl * 8 + 0, epoch, tags_ok);
-            a1 += ld_tag_double(opt.tagw + bl * 8 + 2, epoch, tags_ok);
-            a2 += ld_tag_double(opt.tagw + bl * 8 + 4, epoch, tags_ok);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        if (lane == 0) { opt.loss_out[0] += a0; opt.loss_out[1] += a1; opt.loss_out[2] += a2; opt.loss_out[3] += opt.rows; }
-    }
+    // losses of the whole launch (one warp of CTA 0)
+    if (blockIdx.x == 0 && is_mma_warp && opt.loss_out && tags_ok) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
     // sharded: exchange buffer of rank r = inbox[2 (step parity)][world (sender)][gstride] 8-byte words {float bits, step number}
     const unsigned int xepoch = (unsigned int)opt_step;   // the ranks agree on the optimiser step, not on launch counters
     const int inbox_off = (int)(opt_step & 1) * opt.world * opt.gstride;   // this step's inbox, in words
-    __shared__ int peers_ok;
-    if (tid == 0) peers_ok = 1;   // (made visible by the barriers inside the loop before anybody reads it)
-    for (int sidx = blockIdx.x; sidx < nsl; sidx += nb) {
+    for (int sidx = blockIdx.x; sidx < nsl && tags_ok; sidx += nb) {
         const int p0 = sidx * RC, nc = min(RC, P - p0);
         for (int item = tid; item < nc * RED_SL; item += TC_THREADS) {
             const int sl = item / nc, pi = item - sl * nc;
-            sl_part[sl * RC + pi] = reduce_slice_tagged(reinterpret_cast<const unsigned long long *>(partials), nb, part_stride, p0 + pi, sl, epoch, tags_ok);
+            sl_part[sl * RC + pi] = reduce_slice(partials, nb, part_stride, p0 + pi, sl);
         }
         __syncthreads();
         float gi = 0.f;
@@ -945,27 +1063,29 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 const unsigned long long *in = reinterpret_cast<const unsigned long long *>(opt.peers[opt.rank]) + inbox_off + p0 + tid;
                 float g = 0.f;
                 bool ok = true;
+                const unsigned long long t0 = globaltimer_ns();
                 for (int r0 = 0; r0 < opt.world; r0 += 8) {   // 8 ranks polled together, summed in rank order
                     unsigned long long pv[8];
                     bool all = false;
-                    for (int itp = 0; itp < (1 << 22) && !all; ++itp) {
+                    for (int itp = 0; !all; ++itp) {
                         all = true;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             pv[u] = r0 + u < opt.world ? ld_relaxed_sys_u64(in + (r0 + u) * opt.gstride) : ((unsigned long long)xepoch << 32);
                             all = all && (unsigned int)(pv[u] >> 32) == xepoch;
                         }
+                        if (!all && (itp & 63) == 63 && globaltimer_ns() - t0 > opt.timeout_ns) break;
                     }
                     ok = ok && all;
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (r0 + u < opt.world) g += __uint_as_float((unsigned int)pv[u]);
                 }
-                if (!ok) peers_ok = 0;
+                if (!ok) tail_ok_s = 0;
                 gi = g;
             }
             __syncthreads();
-            if (!peers_ok) { if (tid == 0) atomicExch(status, 3); return; }
+            if (!tail_ok_s) { tags_ok = false; if (tid == 0) atomicExch(status, 3); break; }
         }
         if (tid < nc) {
             opt.grad[p0 + tid] = gi;
@@ -976,30 +1096,40 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             for (int k = 0; k < nc; ++k) ssum += sq[k];
         __syncthreads();
     }
-    if (tid == 0) st_tag_double(opt.tagw + blockIdx.x * 8 + 6, ssum, epoch);
-    TC_SPAN0(1);
-    TC_SPAN0(2);
-    __shared__ float coef_s;
+    // a CTA that failed publishes nothing: the others time out on its squared norm, nobody applies the step
+    if (tid == 0 && tags_ok) st_tag_double(opt.tagw + blockIdx.x * 2, ssum, epoch);
+    TC_SPAN(6);
     if (warp == 0) {
-        // total squared norm in a fixed order: lane l adds the CTAs' (tagged) partials l, l + 32, ...; then a fixed shuffle tree
-        double a = 0.0;
-        for (int k = lane; k < nb; k += 32) a += ld_tag_double(opt.tagw + k * 8 + 6, epoch, tags_ok);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) {
-            const float total = (float)sqrt(a);
-            coef_s = opt.max_norm > 0.f ? fminf(opt.max_norm / (total + 1e-6f), 1.0f) : 1.f;
-            if (blockIdx.x == 0) {
-                if (opt.norm_out) *opt.norm_out = (double)total;
-                double *pw = reinterpret_cast<double *>(opt.clock) + 1;
-                opt.clock[0] = opt_step; pw[0] = opt_p1; pw[1] = opt_p2;
-                reinterpret_cast<unsigned int *>(status)[3] = epoch;   // the launch counter (every CTA read it at its start)
+        if (leader) {
+            // total squared norm in a fixed order; the leader also advances the optimiser clock and the launch counter and
+            // re-arms the arrival counter (every CTA has passed it: it published its squared norm afterwards)
+            const double a = tags_ok ? sum_tagged_doubles(opt.tagw, nb, epoch, lane, opt.timeout_ns, tags_ok) : 0.0;
+            if (lane == 0) {
+                const float total = (float)sqrt(a);
+                const float coef = opt.max_norm > 0.f ? fminf(opt.max_norm / (total + 1e-6f), 1.0f) : 1.f;
+                coef_s = coef;
+                if (!tags_ok) tail_ok_s = 0;
+                else {
+                    st_tag(opt.coefw, __float_as_uint(coef), epoch);
+                    if (opt.norm_out) *opt.norm_out = (double)total;
+                    double *pw = reinterpret_cast<double *>(opt.clock) + 1;
+                    opt.clock[0] = opt_step; pw[0] = opt_p1; pw[1] = opt_p2;
+                    reinterpret_cast<unsigned int *>(status)[3] = epoch;   // the launch counter (every CTA read it at its start)
+                    *opt.count = 0u;
+                }
             }
+        } else if (lane == 0) {
+            if (tags_ok) coef_s = __uint_as_float(wait_tag(opt.coefw, epoch, opt.timeout_ns, tags_ok));
+            if (!tags_ok) tail_ok_s = 0;
         }
     }
-    if (!tags_ok) atomicExch(status, 2);
     __syncthreads();
-    TC_SPAN0(3);
+    TC_SPAN(7);
+    if (!tail_ok_s) {   // some wait timed out: the step is NOT applied by this CTA (status 2 unless a peer wait already said 3)
+        if (tid == 0) atomicCAS(status, 0, 2);
+        TC_SPAN(3);
+        return;
+    }
     {
         const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
         const float step_size = (float)((double)opt.lr / (1.0 - opt_p1)), bc2_sqrt = (float)sqrt(1.0 - opt_p2);
@@ -1063,10 +1193,21 @@ static int tc_grid_max(int64_t b) {
     const int64_t nt = (b + TC_ROWS - 1) / TC_ROWS;
     return (int)(nt < sms ? (nt > 0 ? nt : 1) : sms);
 }
-// header (4 words: status, 2 barrier words, launch counter) | partial rows (8-byte tagged words in the fused step, floats
-// otherwise) | loss partials (4 doubles per CTA) | squared-norm partials (1 double) | tagged scalars (8 words per CTA)
+// header (4 words: status, arrival counter, unused, launch counter) | partial rows (floats, 16-byte aligned rows) | loss partials
+// (4 doubles per CTA) | squared-norm words (2 tagged 8-byte words per CTA) | clip-coefficient words (2)
 static size_t tc_ws_floats(const PolicyLayout &L, int grid) {
-    return 4 + (size_t)2 * grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 2 + (size_t)grid * 16 + 16;
+    return 4 + (size_t)grid * ((L.total + 3) & ~3) + (size_t)grid * 8 + (size_t)grid * 4 + (size_t)grid + 16;
+}
+// bound of the in-kernel waits on other CTAs / other GPUs, wall clock (PRL_TC_TIMEOUT_MS, default 20 s: a stalled peer process
+// - profiler, lazy module load - must not be mistaken for a dead one)
+static unsigned long long tc_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (!ns) {
+        const char *e = getenv("PRL_TC_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 20000.0;
+        ns = (unsigned long long)((ms > 0.0 ? ms : 20000.0) * 1e6);
+    }
+    return ns;
 }
 
 }  // namespace prl
@@ -1102,54 +1243,60 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
     const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
     const size_t smem = tc_smem_bytes(L, NA);
     PRL_REQUIRE(smem <= 227 * 1024, "%s: needs %zu B shared memory (> 227 KB)", who, smem);
-    // ws: [0] sticky status word, [1..2] grid-barrier counters (the caller zeroes the workspace once; the counters are
-    // re-zeroed before every fused launch), then per-CTA partial gradients, loss partials, squared-norm partials
+    PRL_REQUIRE(grid <= TC_MAX_GRID, "%s: grid %d > %d", who, grid, TC_MAX_GRID);
+    // ws: [0] sticky status word, [1] arrival counter, [3] launch counter (the caller zeroes the workspace once), then per-CTA
+    // partial gradients, loss partials, squared-norm words, clip-coefficient words
     int *status = reinterpret_cast<int *>(ws);
     float *partials = ws + 4;
-    double *loss_partials = reinterpret_cast<double *>(partials + (size_t)2 * grid * pstride);
+    double *loss_partials = reinterpret_cast<double *>(partials + (size_t)grid * pstride);
     TcOptimizer opt{};
     if (optp) {
         opt = *optp;
-        opt.sync = reinterpret_cast<unsigned int *>(ws) + 1;
-        opt.sumsq = loss_partials + (size_t)grid * 4;
-        opt.tagw = reinterpret_cast<unsigned long long *>(opt.sumsq + grid);
+        opt.tagw = reinterpret_cast<unsigned long long *>(loss_partials + (size_t)grid * 4);
+        opt.coefw = opt.tagw + (size_t)grid * 2;
+        opt.count = reinterpret_cast<unsigned int *>(ws) + 1;
+        opt.timeout_ns = tc_timeout_ns();
     }
     auto launch = [&](auto kernel) -> int {
         PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;   // the fused tail spins on grid barriers: every CTA must be resident
+        attr[0].id = cudaLaunchAttributeCooperative;   // the fused tail waits on the other CTAs: every CTA must be resident
         attr[0].val.cooperative = optp ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
         PRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
                                     loss_partials, status, opt, qpc));
         return PRL_OK;
     };
-    const int rc = NA == 2 ? launch(k_ppo_grad_tc<2>) : NA == 4 ? launch(k_ppo_grad_tc<4>) : launch(k_ppo_grad_tc<8>);
+    const bool x4 = obs_dim <= 4;
+    const int rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4>) : launch(k_ppo_grad_tc<2, 8>))
+                 : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4>) : launch(k_ppo_grad_tc<4, 8>))
+                           : launch(k_ppo_grad_tc<8, 8>);
     if (rc != PRL_OK) return rc;
     if (getenv("PRL_TC_TIMING")) {
         long long c[32];
         PRL_CUDA(cudaStreamSynchronize(st));
         PRL_CUDA(cudaMemcpyFromSymbol(c, g_tc_clock, sizeof c));
-        fprintf(stderr, "[%s] CTA0 thread 0 cycles: setup %lld | tile 0: trunk fwd + stage F %lld, wait fwd MMA %lld, actor epilogue %lld, stage DZ %lld, "
+        fprintf(stderr, "[%s] CTA0 thread 0 cycles: setup %lld (W1 loads issued %lld, W1 row arrived %lld, parameters in shared memory %lld, pieces stored %lld) | tile 0: trunk fwd + stage F %lld, wait fwd MMA %lld, actor epilogue %lld, stage DZ %lld, "
                         "critic epilogue %lld, wait actor MMA + stage DZ %lld, wait critic MMA %lld, trunk bwd + stage %lld | all tiles %lld, final MMA wait %lld, "
                         "readout %lld, tail %lld | kernel %lld\n", who,
-                c[1] - c[0], c[2] - c[1], c[4] - c[2], c[5] - c[4], c[6] - c[5], c[8] - c[6], c[9] - c[8], c[11] - c[9], c[12] - c[11], c[13] - c[1],
+                c[1] - c[0], c[19] - c[0], c[20] - c[0], c[17] - c[0], c[18] - c[0], c[2] - c[1], c[4] - c[2], c[5] - c[4], c[6] - c[5], c[8] - c[6], c[9] - c[8], c[11] - c[9], c[12] - c[11], c[13] - c[1],
                 c[14] - c[13], c[15] - c[14], c[16] - c[15], c[16] - c[0]);
-        static unsigned long long sp[160 * 4 + 8];
+        static unsigned long long sp[160 * 8];
         PRL_CUDA(cudaMemcpyFromSymbol(sp, g_tc_span, sizeof sp));
-        unsigned long long t0 = ~0ull, s_max = 0, e1_min = ~0ull, e1_max = 0, e2_max = 0, e3_max = 0;
-        for (int c2 = 0; c2 < grid && c2 < 160; ++c2) {
-            t0 = sp[c2 * 4] < t0 ? sp[c2 * 4] : t0; s_max = sp[c2 * 4] > s_max ? sp[c2 * 4] : s_max;
-            e1_min = sp[c2 * 4 + 1] < e1_min ? sp[c2 * 4 + 1] : e1_min; e1_max = sp[c2 * 4 + 1] > e1_max ? sp[c2 * 4 + 1] : e1_max;
-            e2_max = sp[c2 * 4 + 2] > e2_max ? sp[c2 * 4 + 2] : e2_max; e3_max = sp[c2 * 4 + 3] > e3_max ? sp[c2 * 4 + 3] : e3_max;
-        }
-        fprintf(stderr, "[%s] grid %d wall clock (ns from the first CTA start): last CTA start %llu | tiles done: first %llu, last %llu | partials written %llu | "
-                        "kernel end %llu | CTA0: start %llu tiles %llu end %llu\n", who, grid, s_max - t0, e1_min - t0, e1_max - t0, e2_max - t0, e3_max - t0,
-                sp[0] - t0, sp[1] - t0, sp[3] - t0);
-        if (optp) fprintf(stderr, "[%s] CTA0 tail: barrier 1 passed %llu, slice reduced %llu, barrier 2 passed %llu, norm known %llu, end %llu\n", who, sp[640] - t0,
-                          sp[641] - t0, sp[642] - t0, sp[643] - t0, sp[3] - t0);
+        unsigned long long t0 = ~0ull, mn[8], mx[8];
+        for (int k = 0; k < 8; ++k) { mn[k] = ~0ull; mx[k] = 0; }
+        for (int c2 = 0; c2 < grid && c2 < 160; ++c2) t0 = sp[c2 * 8] < t0 ? sp[c2 * 8] : t0;
+        for (int c2 = 0; c2 < grid && c2 < 160; ++c2)
+            for (int k = 0; k < 8; ++k) {
+                const unsigned long long v = sp[c2 * 8 + k] - t0;
+                mn[k] = v < mn[k] ? v : mn[k]; mx[k] = v > mx[k] ? v : mx[k];
+            }
+        fprintf(stderr, "[%s] grid %d wall clock, ns from the first CTA start, min..max over CTAs: start %llu..%llu | tiles done %llu..%llu | partials written "
+                        "%llu..%llu | kernel end %llu..%llu\n", who, grid, mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3]);
+        if (optp) fprintf(stderr, "[%s] tail: arrival counted %llu..%llu | all arrivals seen %llu..%llu | slices reduced %llu..%llu | norm known %llu..%llu\n", who,
+                          mn[4], mx[4], mn[5], mx[5], mn[6], mx[6], mn[7], mx[7]);
     }
     if (!optp) k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
     return check_launch(who);
@@ -1229,9 +1376,9 @@ int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream) {
     PRL_REQUIRE(ws && status_host, "prl_ppo_grad_tc_status: bad arguments");
     PRL_CUDA(cudaMemcpyAsync(status_host, ws, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    // a timed-out grid barrier leaves its arrival count behind: clear it so that the workspace can be used again
+    // a timed-out launch leaves its arrival count behind: clear it so that the workspace can be used again
     if (*status_host == 2 || *status_host == 3)
-        PRL_CUDA(cudaMemsetAsync(const_cast<float *>(ws) + 1, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream));
+        PRL_CUDA(cudaMemsetAsync(const_cast<float *>(ws) + 1, 0, sizeof(unsigned int), (cudaStream_t)stream));
     return PRL_OK;
 }
 
