@@ -211,8 +211,7 @@ def run_b200(args):
     ppo.graph_collectives = os.environ.get("PRL_GRAPH_COLLECTIVES", "1") == "1"   # NCCL allreduce captured in the graph too
     # sharded runs: gradient exchange over NVLink peer memory inside the step kernel (0 = NCCL allreduce between grad and AdamW)
     ppo.peer_exchange = os.environ.get("PRL_PEER_EXCHANGE", "1") == "1"
-    ppo._seed += rank  # different action noise per shard
-    t.manual_seed(1234 + rank)  # different env reset stream per shard
+    # (sharded: PPO broadcasts rank 0's replica at construction and keys the sampling / reset streams by rank - prl_b200.dist.rank_seed)
     ap = AsyncPPO(env=prl_b200.make("CartPole-v1", max_episode_steps=T), ppo=ppo, num_envs=E, steps=1)
     flush = t.empty(256 << 20, dtype=t.uint8, device=dev)
     rng = np.random.default_rng(1234 + rank)
@@ -257,6 +256,29 @@ def run_b200(args):
         counts = {k_: v - counts0.get(k_, 0) for k_, v in _lib.CALL_COUNTS.items() if v - counts0.get(k_, 0)}
         return float(tot.item()), float(ms.item()), counts, prof, (w0, w1)
 
+    # sharded parity, visible to the driver on every scaling run: ONE rollout consumed twice from the same replica state - by the
+    # in-kernel peer-memory exchange (the timed path) and by the NCCL-allreduce path - must give the same weights (bit-identical
+    # at 2 ranks: a two-addend sum is commutative; at more ranks NCCL's reduction order differs from the kernel's rank order)
+    p2p_check = None
+    if comm is not None and ppo.peer_exchange:
+        ap.worker()
+        n_rows = ppo.memory._dev_count
+        keep = [x.clone() for x in (ppo.policy.flat, ppo.policy_old.flat, ppo.optimizer.exp_avg, ppo.optimizer.exp_avg_sq, ppo.optimizer.step_dev)]
+        k0, cnt0, ppo.k_epochs = ppo.k_epochs, ppo.optimizer.step_count, 1
+        res = []
+        for peer in (True, False):
+            for dst, src in zip((ppo.policy.flat, ppo.policy_old.flat, ppo.optimizer.exp_avg, ppo.optimizer.exp_avg_sq, ppo.optimizer.step_dev), keep):
+                dst.copy_(src)
+            ppo.optimizer.step_count = cnt0
+            ppo.memory._dev_count = n_rows          # the same rows again (learn() only reads them)
+            ppo.peer_exchange = peer
+            ppo.learn()
+            res.append(ppo.policy.flat.clone())
+        ppo.peer_exchange, ppo.k_epochs = True, k0
+        diff = (res[0] - res[1]).abs().max().reshape(1).double()
+        comm.allreduce_max_(diff)
+        p2p_check = {"optimizer_steps": int(ppo.optimizer.step_count - cnt0), "max_abs_weight_diff_vs_nccl_path": float(diff.item()),
+                     "peer_path_used": bool(ppo._p2p_ok)}
     for _ in range(args.warmup):
         step(False)
     step(True)  # touch the e2e path once
@@ -265,6 +287,15 @@ def run_b200(args):
     n_dev, ms_dev, counts, _, (w0, w1) = timed(False, args.steps, profile=False)
     clk = clocks.summary(w0, w1) if clocks else None
     n_e2e, ms_e2e, _, _, _ = timed(True, args.steps, profile=False)
+    # sharded: the replicas must still be identical after the timed region (weights and AdamW moments, bit for bit)
+    replicas_identical = None
+    if comm is not None:
+        import torch.distributed as td
+
+        mine = t.cat([ppo.policy.flat, ppo.policy_old.flat, ppo.optimizer.exp_avg, ppo.optimizer.exp_avg_sq])
+        allw = [t.empty_like(mine) for _ in range(world)]
+        td.all_gather(allw, mine)
+        replicas_identical = all(t.equal(allw[0], w) for w in allw[1:]) and bool(t.isfinite(mine).all())
     # kernel attribution: ONE more step of the same workload, launch by launch (no CUDA graph), every entry-point call
     # bracketed by CUDA events on the launching stream
     ppo.use_cuda_graph = False
@@ -331,6 +362,8 @@ def run_b200(args):
         "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_states.numel() * 8),
                 "d2h_bytes_per_step": int(host_weights.numel() * 4 + 16 + 16), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": _lib.launches(counts),
+        "replicas_identical": replicas_identical,
+        "sharded_parity": p2p_check,
         "calls": counts,
         "clocks": clk,
         "roofline": roof,

@@ -154,7 +154,7 @@ class AdamW:
 
 
 def clip_grad_norm(grads, max_norm):
-    total = t.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    total = t.sqrt(sum((g.double() ** 2).sum() for g in grads)).to(grads[0].dtype)
     coef = t.clamp(max_norm / (total + 1e-6), max=1.0)
     return [g * coef for g in grads], total
 
@@ -194,11 +194,18 @@ def ppo_loss(p, is_continuous, s, a, old_logp, adv, ret, clip):
 
 
 def learn(params, is_continuous, mem, *, lr, k_epochs, policy_clip, gae_lambda, gamma, mini_batch_size,
-          rnd_params=None, beta=0.001, opt=None, rnd_opt=None, trace=None):
+          rnd_params=None, beta=0.001, opt=None, rnd_opt=None, trace=None, schedule=None, dtype=t.float32):
     """One PPO.learn() over `mem` = dict(states [N,O], actions, rewards [N], dones [N]) float32.
-    Mutates `params` (and rnd_params) in place; returns the per-minibatch mean losses."""
+    Mutates `params` (and rnd_params) in place; returns the per-minibatch mean losses.
+
+    `schedule` (optional): list of index arrays, one per minibatch, replacing the reference's sequential chunks
+    `[k*mb, (k+1)*mb)` in the update loop - "the reference fed the same permutation" of SURVEY.md H7, used to check
+    env-sharded runs whose global minibatch k is the union of every rank's k-th local chunk.  Old-policy evaluation,
+    GAE and the advantage normalisation do not depend on it (row-wise / segment-wise / global).
+    `dtype=torch.float64` evaluates the same update in double precision (the truth the float32 runs are judged by;
+    GAE stays the reference's float32 loop); `params` must then be float64 tensors."""
     keys = param_keys(is_continuous)
-    s = t.as_tensor(mem["states"], dtype=t.float32); a = t.as_tensor(mem["actions"], dtype=t.float32)
+    s = t.as_tensor(mem["states"], dtype=t.float32).to(dtype); a = t.as_tensor(mem["actions"], dtype=t.float32).to(dtype)
     N, mb = len(s), mini_batch_size
     old = {k: v.clone() for k, v in params.items()}
     with t.no_grad():
@@ -214,8 +221,8 @@ def learn(params, is_continuous, mem, *, lr, k_epochs, policy_clip, gae_lambda, 
         if rnd_opt is None:
             rnd_opt = AdamW([rnd_params[f"pred_net.{k}"] for k in RND_KEYS], lr=1e-3)
         rnd_update(rnd_params, rnd_opt, s, mb)
-    v_np = old_values.numpy()
-    returns = t.from_numpy(compute_gae(rewards, mem["dones"], v_np, v_np[-1], gamma, gae_lambda))
+    v_np = old_values.float().numpy()
+    returns = t.from_numpy(compute_gae(rewards, mem["dones"], v_np, v_np[-1], gamma, gae_lambda)).to(dtype)
     adv = returns - old_values
     adv = (adv - adv.mean()) / (adv.std() + 1e-8)
     if trace is not None:
@@ -224,9 +231,9 @@ def learn(params, is_continuous, mem, *, lr, k_epochs, policy_clip, gae_lambda, 
     if opt is None:
         opt = AdamW([params[k] for k in keys], lr=lr)
     losses = []
+    chunks = [slice(i, i + mb) for i in range(0, N, mb)] if schedule is None else [t.as_tensor(ix, dtype=t.long) for ix in schedule]
     for _ in range(k_epochs):
-        for i in range(0, N, mb):
-            sl = slice(i, i + mb)
+        for sl in chunks:
             for k in keys:
                 params[k].requires_grad_(True)
             loss = ppo_loss(params, is_continuous, s[sl], a[sl], old_logp[sl], adv[sl], returns[sl], policy_clip)

@@ -16,6 +16,7 @@ import torch as t
 from tqdm import tqdm
 
 import AsyncTools.utils as utils
+from prl_b200 import dist as pdist
 from prl_b200 import ops
 from prl_b200._lib import require_cuda
 from prl_b200.envs import describe
@@ -158,6 +159,8 @@ class EnvVectorizer:
         self.observation_space = env.observation_space
         self.sim = ops.EnvState(self.desc.env_id, self.num_envs, self.desc.max_episode_steps)
         self.seed = int(t.randint(0, 2 ** 62, (1,)).item())  # reset stream of the Philox generator
+        if pdist.active() is not None:   # env-sharded run: identically seeded ranks must not reset their shards identically
+            self.seed = pdist.rank_seed(self.seed, pdist.active().rank)
         self.episode = 0   # incremented by every reset(); selects the reset / action random streams
         self.t = 0         # steps since reset()
 

@@ -19,7 +19,7 @@ class _Field:
         self._owner, self._name, self._host = owner, name, []
 
     def __len__(self):
-        return len(self._host) + self._owner._dev_count
+        return len(self._host) + (0 if self._name in self._owner._dev_cleared else self._owner._dev_count)
 
     def append(self, item):
         self._owner._host_after_device()
@@ -36,7 +36,7 @@ class _Field:
     def _rows(self):
         out = list(self._host)
         t = self._owner._dev.get(self._name)
-        if t is not None and self._owner._dev_count:
+        if t is not None and self._owner._dev_count and self._name not in self._owner._dev_cleared:
             arr = t[: self._owner._dev_count].cpu().numpy()
             if arr.ndim == 2 and arr.shape[1] == 1 and self._name == "actions" and self._owner._scalar_actions:
                 arr = arr[:, 0]
@@ -47,16 +47,36 @@ class _Field:
         return iter(self._rows())
 
     def __getitem__(self, i):
+        """Items like the reference's list: a single index downloads that one row, not the whole field."""
+        nh, nd = len(self._host), len(self) - len(self._host)
+        if isinstance(i, (int, np.integer)):
+            j = int(i) + (nh + nd if i < 0 else 0)
+            if not 0 <= j < nh + nd:
+                raise IndexError("memory field index out of range")
+            if j < nh:
+                return self._host[j]
+            row = self._owner._dev[self._name][j - nh].cpu().numpy()
+            if self._name == "actions" and row.shape == (1,) and self._owner._scalar_actions:
+                row = row[0]
+            return row
         return self._rows()[i]
 
     def __delitem__(self, i):
         if i == slice(None, None, None):
-            self._host.clear()
+            self.clear()
         else:
             raise TypeError("only `del field[:]` is supported")
 
     def clear(self):
+        """`del memory.states[:]` (the reference's own Memory.clear idiom, Memory.py:26-30) empties the device rows of this
+        field too; once all four fields have been emptied the device store is reset."""
         self._host.clear()
+        own = self._owner
+        if own._dev_count:
+            own._dev_cleared.add(self._name)
+            if len(own._dev_cleared) == len(FIELDS):
+                own._dev_count = 0
+                own._dev_cleared.clear()
 
     def __repr__(self):
         return f"<{self._name}: {len(self)} items>"
@@ -68,7 +88,10 @@ class Memory:
         self._dev_count = 0
         self._dev_cap = 0
         self._scalar_actions = True
-        self._total = None  # device int64 scratch written by the transfer kernel
+        self._total = None  # device int64 written by the transfer kernel: rows in the store after the last transfer
+        self._expect_total = None   # what the host believes that number is (checked by verify_transfers)
+        self._overflow = None       # the rollout buffer's overflow flag of the last transfer
+        self._dev_cleared = set()   # fields emptied one by one through `del field[:]`
         self._fields = {n: _Field(self, n) for n in FIELDS}
 
     # list-like attributes, assignable like the reference's plain lists
@@ -83,7 +106,7 @@ class Memory:
         self._fields[name]._host = list(value)
 
     def _host_after_device(self):
-        if self._dev_count:
+        if self._dev_count and not self._dev_cleared:
             raise RuntimeError("mixing host pushes after a device transfer is not supported; call learn() or clear() first")
 
     def push(self, state, action, reward, done):
@@ -93,8 +116,23 @@ class Memory:
 
     def clear(self):
         for f in self._fields.values():
-            f.clear()
+            f._host.clear()
         self._dev_count = 0
+        self._dev_cleared.clear()
+
+    def verify_transfers(self):
+        """Host-synchronising check that the device agrees with the host's bookkeeping: the transfer kernel's row total equals
+        the count the host derived from the rollout's step score (a capacity miscount would otherwise silently truncate the
+        batch), and no rollout buffer overflowed.  PPO.learn() calls it where it synchronises anyway."""
+        if self._expect_total is not None:
+            got = int(self._total.item())
+            want, self._expect_total = self._expect_total, None
+            if got != want:
+                raise RuntimeError(f"Memory: the device transferred {got} rows but the host expected {want}")
+        if self._overflow is not None:
+            ov, self._overflow = int(self._overflow.item()), None
+            if ov:
+                raise RuntimeError("Memory: a rollout buffer overflowed its time capacity (transitions were dropped)")
 
     # ---- device side -------------------------------------------------------------------------------------------
     def reserve(self, capacity, obs_dim, act_width, device):
@@ -152,3 +190,4 @@ class Memory:
         self._scalar_actions = scalar_actions
         buf.transfer(self._dev["states"], self._dev["actions"], self._dev["rewards"], self._dev["dones"], base, self._total)
         self._dev_count = base + int(n_new)
+        self._expect_total, self._overflow = self._dev_count, buf.overflow

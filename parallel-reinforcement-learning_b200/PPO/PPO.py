@@ -92,6 +92,38 @@ class PPO:
         self.graph_collectives = False  # also capture the per-minibatch gradient allreduce (NCCL) in the epoch graph
         self.use_cuda_graph = False   # capture each epoch of learn() in a CUDA graph (single process, >= 16 optimiser steps)
         self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
+        self._ws_owner = None         # which update path's header lives in self._ws
+        self._p2p_ok = None           # sharded: can the ranks exchange gradients over peer memory (agreed once, collectively)
+        # sharded (one process per GPU, prl_b200.dist active): only gradients are exchanged afterwards, so every replica must
+        # START identical - rank 0's networks, optimiser state and seed are broadcast once, here or at the first learn()
+        self._replicas_synced = False
+        if pdist.active() is not None:
+            self.sync_replicas(pdist.active())
+
+    # ------------------------------------------------------------------------------------------------ sharding
+    def sync_replicas(self, comm) -> None:
+        """Collective.  Make every rank's replica identical to rank 0's: policy, policy_old, RND target / predictor, AdamW
+        moments and step clocks.  The sampling seed becomes rank_seed(rank 0's seed, rank): the same on-device Philox generator
+        keyed differently per shard, so identically seeded processes do not draw identical action noise."""
+        bufs = [self.policy.flat, self.policy_old.flat, self.optimizer.exp_avg, self.optimizer.exp_avg_sq, self.optimizer.step_dev]
+        if self.use_RND:
+            bufs += [self.rnd.target_flat, self.rnd.pred_flat, self.rnd.optimizer.exp_avg, self.rnd.optimizer.exp_avg_sq, self.rnd.optimizer.step_dev]
+        for b in bufs:
+            comm.broadcast_(b, src=0)
+        meta = t.tensor([self._seed, self.optimizer.step_count, self.rnd.optimizer.step_count if self.use_RND else 0],
+                        dtype=t.int64, device=self.device)
+        comm.broadcast_(meta, src=0)
+        seed0, self.optimizer.step_count, rnd_steps = (int(x) for x in meta.cpu())
+        if self.use_RND:
+            self.rnd.optimizer.step_count = rnd_steps
+        self._seed = pdist.rank_seed(seed0, comm.rank)
+        self._replicas_synced = True
+
+    def close(self) -> None:
+        """Release the peer-memory exchange buffers of a sharded run (collective; see prl_b200.dist.PeerExchange.close)."""
+        if self._xch is not None:
+            self._xch.close()
+            self._xch = None
 
     # ------------------------------------------------------------------------------------------------ acting
     def _action_scale(self) -> float:
@@ -147,6 +179,8 @@ class PPO:
                 return
             if min(n_all) == 0:
                 raise RuntimeError(f"sharded learn(): a rank holds no transitions (rows per rank: {n_all})")
+            if not self._replicas_synced:
+                self.sync_replicas(comm)
         O, A, cont = self.observ_dim, self.action_dim, self.is_continuous
         AW = A if cont else 1
         states, actions, rewards, dones = self.memory.device_view(O, AW, self.device)
@@ -201,13 +235,23 @@ class PPO:
         need = (ops.update_tc_ws_floats if use_tc else ops.update_ws_floats)(cont, O, A, min(mb_local, N))
         if self._ws is None or self._ws.numel() < need:
             self._ws = t.zeros(need, dtype=t.float32, device=self.device)
+        elif self._ws_owner != self.update_path:
+            self._ws[:4].zero_()   # the tensor path keeps its status word / arrival counter / launch counter in the header; the fp32 path writes partials there
+        self._ws_owner = self.update_path
         steps = self.k_epochs * n_mb
 
         fused = use_tc and comm is None and self.fused_optimizer   # gradient + clip + AdamW in one cooperative launch
-        # sharded: the same single launch, with the gradient exchange over NVLink peer memory inside it (no NCCL per step)
+        # sharded: the same single launch, with the gradient exchange over NVLink peer memory inside it (no NCCL per step) -
+        # when every rank sits on this host and all GPU pairs have peer access; otherwise the NCCL allreduce path below
         p2p = use_tc and comm is not None and self.fused_optimizer and self.peer_exchange
+        if p2p:
+            if self._p2p_ok is None:
+                self._p2p_ok = pdist.peer_access_possible(comm)
+            p2p = self._p2p_ok
         if p2p and self._xch is None:
             self._xch = pdist.PeerExchange(comm, cont, O, A)
+        # a failed step (an in-kernel wait that timed out) must not leave a half-applied update behind: keep what is needed to roll back
+        snap = (self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone(), self.optimizer.step_dev.clone(), self.optimizer.step_count) if use_tc else None
 
         def minibatch_step(k, loss_slot):
             lo, hi = min(k * mb_local, N), min((k + 1) * mb_local, N)
@@ -278,10 +322,21 @@ class PPO:
         if pbar is not None:
             pbar.close()
         status = ops.ppo_grad_tc_status(self._ws) if use_tc else 0
+        self.memory.verify_transfers()   # (the status read above synchronised the stream: the transfer totals are final)
+        if comm is not None and use_tc:
+            # every rank learns about a failure anywhere, so that all of them raise together instead of hanging in the next collective
+            st = t.tensor([status], dtype=t.int32, device=self.device)
+            comm.allreduce_max_(st)
+            status = int(st.item())
         if status != 0:
-            raise RuntimeError("tensor-core update failed: " + {1: "an MMA phase never completed (mbarrier timeout)",
-                                                                  2: "grid barrier timed out",
-                                                                  3: "a peer rank never signalled its gradient"}.get(status, f"status {status}"))
+            # roll back to the state before this learn(): weights from policy_old (PPO.py:258-260 has not run yet), moments and clocks
+            self.policy.flat.copy_(self.policy_old.flat)
+            self.optimizer.exp_avg.copy_(snap[0]); self.optimizer.exp_avg_sq.copy_(snap[1]); self.optimizer.step_dev.copy_(snap[2])
+            self.optimizer.step_count = snap[3]
+            self._ws[:4].zero_()
+            raise RuntimeError("tensor-core update failed on some rank (weights and optimiser state rolled back to the start of learn()): " +
+                               {1: "an MMA phase never completed (mbarrier timeout)", 2: "a wait on another CTA timed out",
+                                3: "a peer rank never signalled its gradient"}.get(status, f"status {status}"))
         self.policy_old.flat.copy_(self.policy.flat)  # PPO.py:258-260
 
     # ------------------------------------------------------------------------------------------------ checkpoints

@@ -32,6 +32,15 @@ class Comm:
         td.all_reduce(tensor, op=td.ReduceOp.MAX, group=self.group)
         return tensor
 
+    def broadcast_(self, tensor: torch.Tensor, src: int = 0) -> torch.Tensor:
+        td.broadcast(tensor, src=src, group=self.group)
+        return tensor
+
+    def allgather_obj(self, value) -> list:
+        out = [None] * self.world_size
+        td.all_gather_object(out, value, group=self.group)
+        return out
+
     def allgather_int(self, value: int) -> list[int]:
         out = [None] * self.world_size
         td.all_gather_object(out, int(value), group=self.group)
@@ -85,16 +94,41 @@ def active() -> Comm | None:
     return _ACTIVE
 
 
+RANK_STRIDE = 0x9E3779B97F4A7C15   # odd 64-bit constant: rank r's random streams are keyed seed + r * RANK_STRIDE
+
+
+def rank_seed(seed: int, rank: int) -> int:
+    """The seed of rank `rank`'s Philox streams (action sampling, env resets) derived from the job's seed: identically seeded
+    ranks must not draw identical noise for their shards."""
+    return (int(seed) + int(rank) * RANK_STRIDE) & ((1 << 62) - 1)
+
+
+def peer_access_possible(comm: Comm) -> bool:
+    """True when the in-kernel gradient exchange can be used: every rank of the group runs on this host, every pair of
+    their GPUs has peer access, and they are distinct devices - agreed by all ranks (one allgather), so that either
+    every rank takes the peer-memory path or every rank falls back to the NCCL allreduce."""
+    import socket
+
+    dev = torch.cuda.current_device()
+    info = comm.allgather_obj((socket.gethostname(), dev))
+    ok = len({h for h, _ in info}) == 1 and len({d for _, d in info}) == len(info)
+    if ok:
+        ok = all(d == dev or torch.cuda.can_device_access_peer(dev, d) for _, d in info)
+    return all(comm.allgather_obj(bool(ok)))
+
+
 class PeerExchange:
     """Per-rank gradient exchange buffers shared across the GPUs of one node through CUDA IPC (NVLink / NVSwitch peer
     memory): what prl_ppo_step_tc_p2p sums over instead of calling an NCCL allreduce.  `table` is a device int64 tensor
-    holding the `world_size` buffer addresses as seen from this process (own buffer at [rank])."""
+    holding the `world_size` buffer addresses as seen from this process (own buffer at [rank]).  Only construct it when
+    `peer_access_possible(comm)`; `close()` (collective) unmaps the peers' buffers and frees the own one."""
 
     def __init__(self, comm: Comm, is_continuous: bool, observ_dim: int, action_dim: int):
         import ctypes as C
 
         from . import _lib
 
+        self.comm = comm
         self.rank, self.world_size = comm.rank, comm.world_size
         nbytes = int(_lib.fn("prl_p2p_exchange_bytes")(int(is_continuous), observ_dim, action_dim, self.world_size))
         own = C.c_void_p()
@@ -114,3 +148,34 @@ class PeerExchange:
                 ptrs.append(p.value)
         self.table = torch.tensor(ptrs, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
         comm.barrier()   # every rank has mapped every buffer before anybody signals through them
+
+    def close(self):
+        """Collective: after a barrier (nobody is still signalling through the buffers) close the peers' mappings and free
+        the own buffer.  Idempotent."""
+        from . import _lib
+
+        if self._own is None:
+            return
+        torch.cuda.synchronize()
+        try:
+            self.comm.barrier()
+        except Exception:   # the process group is already gone (interpreter shutdown): still release the local resources
+            pass
+        for p in self._opened:
+            _lib.call("prl_p2p_close_handle", p)
+        self._opened = []
+        _lib.call("prl_p2p_free", self._own)
+        self._own, self.table = None, None
+
+    def __del__(self):
+        # no collective in a finaliser: only release what belongs to this process if close() was never called
+        try:
+            from . import _lib
+
+            if getattr(self, "_own", None) is not None:
+                for p in self._opened:
+                    _lib.fn("prl_p2p_close_handle")(p)
+                _lib.fn("prl_p2p_free")(self._own)
+                self._own = None
+        except Exception:
+            pass

@@ -30,16 +30,19 @@ def bits(a):
     return a.view({4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize])
 
 
-def close_weights(got, want, frac=0.999):
-    """Post-update weights: 1e-5 relative (+2e-6 absolute) - the north_star bar - on >= 99.9% of the components, and
-    3e-5 absolute on the rest.  The escape hatch is AdamW's conditioning, not slack: a component whose gradient is
-    near zero moves by lr * m / sqrt(v) with m / sqrt(v) decided by rounding noise, and the REFERENCE's own float32
-    result sits 8e-6 away from the float64 evaluation of the same update there
-    (tests/test_oracle.py::test_reference_float32_update_is_conditioned_at_1e5)."""
+def close_weights(got, want, frac=1.0, dmax=1e-6):
+    """Post-update weights: 1e-5 relative (+2e-6 absolute) - the north_star bar - on a fraction `frac` of the components and
+    `dmax` absolute on all of them.  The defaults (every component, 1e-6) are what the tensor-core path achieves on every
+    fixture (measured: max |diff| 1.2e-7 .. 3.6e-7, printed by the tests).  The continuous fixture (12 AdamW steps on the
+    fp32-FMA path) is checked at frac = 0.9995, dmax = 1e-5 (achieved: 99.99 %, 6.9e-6): that escape hatch is AdamW's
+    conditioning, not slack - a component whose gradient is near zero moves by lr * m / sqrt(v) with m / sqrt(v) decided by
+    rounding noise, and the REFERENCE's own float32 result sits 8e-6 away from the float64 evaluation of the same update
+    there (tests/test_oracle.py::test_reference_float32_update_is_conditioned_at_1e5)."""
     d = np.abs(got.astype(np.float64) - want.astype(np.float64))
     ok = d <= 1e-5 * np.abs(want) + 2e-6
     assert ok.mean() >= frac, (ok.mean(), d.max())
-    assert d.max() <= 3e-5, d.max()
+    assert d.max() <= dmax, d.max()
+    return float(ok.mean()), float(d.max()), float((d / (np.abs(want) + 1e-3)).max())
 
 
 def make_ppo(api, g, **kw):
@@ -60,7 +63,7 @@ def make_ppo(api, g, **kw):
 
 @pytest.mark.parametrize("name,roll", [("discrete", "cartpole"), ("continuous", "pendulum"), ("rnd", "acrobot"),
                                        ("discrete_1step", "cartpole"), ("continuous_1step", "pendulum")])
-def test_learn_matches_reference_post_update_weights(api, golden, name, roll):
+def test_learn_matches_reference_post_update_weights(api, golden, name, roll, capsys):
     """PPO.learn() on the reference's memory contents -> the reference's post-update weights and AdamW moments."""
     g, r = golden("learn_" + name), golden("rollout_" + roll)
     ppo = make_ppo(api, g)
@@ -72,18 +75,22 @@ def test_learn_matches_reference_post_update_weights(api, golden, name, roll):
     ppo.learn()
     assert len(ppo.memory.states) == 0
     got = ppo.policy.flat.cpu().numpy()
-    close_weights(got, g["post_flat"])
+    tol = dict(frac=0.9995, dmax=1e-5) if name == "continuous" else {}
+    fr, dmax, rmax = close_weights(got, g["post_flat"], **tol)
+    with capsys.disabled():
+        print(f"\n[parity] learn_{name} ({ppo.update_path} path, {ppo.optimizer.step_count} optimiser steps) post-update weights vs the REAL "
+              f"reference: {100 * fr:.2f} % of components within 1e-5*|w| + 2e-6, max |diff| {dmax:.2e}, max |diff| / (|w| + 1e-3) {rmax:.2e}")
     assert np.array_equal(ppo.policy_old.flat.cpu().numpy(), got)
     for k in g.files:  # through the state_dict keys as well (checkpoint layout)
         if k.startswith("post."):
-            close_weights(ppo.policy.state_dict()[k[5:]].cpu().numpy().ravel(), g[k].ravel(), frac=0.99)
+            close_weights(ppo.policy.state_dict()[k[5:]].cpu().numpy().ravel(), g[k].ravel(), frac=0.99 if name == "continuous" else 1.0, dmax=tol.get("dmax", 1e-6))
     # AdamW moments: sums of signed gradients, so components near zero carry cancellation noise - 1e-5 of the largest
     for got_m, want_m in ((ppo.optimizer.exp_avg, g["post_exp_avg"]), (ppo.optimizer.exp_avg_sq, g["post_exp_avg_sq"])):
         np.testing.assert_allclose(got_m.cpu().numpy(), want_m, rtol=1e-4, atol=1e-5 * np.abs(want_m).max())
     if bool(g["use_rnd"]):
         for k in g.files:
             if k.startswith("rnd_post."):
-                close_weights(ppo.rnd.state_dict()[k[9:]].cpu().numpy().ravel(), g[k].ravel(), frac=0.99)
+                close_weights(ppo.rnd.state_dict()[k[9:]].cpu().numpy().ravel(), g[k].ravel())
     # loss of the first minibatch step vs the oracle's restatement of the reference loss
     l = ppo.last_losses[0].cpu().numpy()
     mb = int(g["mini_batch_size"])
@@ -94,6 +101,40 @@ def test_learn_matches_reference_post_update_weights(api, golden, name, roll):
                                float(g["policy_clip"])))
     if not bool(g["use_rnd"]):  # with RND the golden advantages were recorded after reward mixing; loss checked above via weights
         assert (l[0] + 0.5 * l[1] - 0.01 * l[2]) / l[3] == pytest.approx(want, rel=1e-5, abs=1e-6)
+
+
+def test_learn_large_minibatch_matches_oracle_learn(api, capsys):
+    """PPO.learn() at BASELINE's minibatch size: >= 2^17 rows from a sampled CartPole rollout, mini_batch_size = 65 536
+    (two full minibatches of 3.5 tiles per CTA + a partial one), 2 epochs = 6+ optimiser steps through the fused tcgen05
+    step kernel - against oracle.ppo.learn on the same memory contents, in float32 (what the reference runs) and in
+    float64 (the truth both float32 runs are judged by)."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    t.manual_seed(11)
+    ppo = P.PPO(is_continuous=False, observ_dim=4, action_dim=2, k_epochs=2, batch_size=1024, mini_batch_size=65536, lr=1e-3)
+    ppo.show_progress = False
+    assert ppo.update_path == "tensor"
+    ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=64), ppo=ppo, num_envs=8192, steps=1)
+    ap.worker()
+    s, a, r, dn = ppo.memory.device_view(4, 1, ppo.device)
+    N = s.shape[0]
+    assert N >= 1 << 17, N
+    mem = dict(states=s.cpu().numpy(), actions=a.cpu().numpy()[:, 0], rewards=r.cpu().numpy(), dones=dn.cpu().numpy())
+    init = ppo.policy.flat.cpu().numpy().copy()
+    ppo.learn()
+    got = ppo.policy.flat.cpu().numpy()
+    kw = dict(lr=1e-3, k_epochs=2, policy_clip=0.2, gae_lambda=0.95, gamma=0.995, mini_batch_size=65536)
+    p32 = oppo.unflatten(init, False, 4, 2)
+    oppo.learn(p32, False, mem, **kw)
+    p64 = {k: v.double() for k, v in oppo.unflatten(init, False, 4, 2).items()}
+    oppo.learn(p64, False, mem, dtype=t.float64, **kw)
+    w32 = oppo.flatten(p32, False).numpy(); w64 = oppo.flatten(p64, False).numpy()
+    fr, dmax, rmax = close_weights(got, w32)
+    d64 = np.abs(got - w64).max(); o64 = np.abs(w32.astype(np.float64) - w64).max()
+    with capsys.disabled():
+        print(f"\n[parity] learn() N={N}, mini_batch 65 536, {ppo.optimizer.step_count} optimiser steps: vs oracle float32 {100 * fr:.2f} % within "
+              f"1e-5*|w| + 2e-6, max |diff| {dmax:.2e}; vs oracle float64 max |diff| {d64:.2e} (oracle float32 itself: {o64:.2e})")
+    assert d64 <= 1e-6, d64   # achieved 2.8e-7 - the same distance the float32 oracle keeps from the float64 one
+    assert not np.array_equal(got, init)
 
 
 def test_learn_with_cuda_graph_epochs_is_bit_identical(api):

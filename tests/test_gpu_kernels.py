@@ -470,32 +470,53 @@ def test_tensor_core_ppo_grad_matches_oracle(ops, golden, name, roll):
             off += n
 
 
-def test_tensor_core_ppo_grad_large_batch_matches_fp32_kernel(ops, golden):
-    """65 537 rows: many tiles per CTA (tensor-memory accumulation across tiles), a ragged last tile, both kernels on
-    the same random inputs.  Bar: 3e-5 of the largest gradient component."""
+def test_tensor_core_ppo_grad_large_batch_matches_fp64_oracle(ops, golden, capsys):
+    """65 537 rows (BASELINE's minibatch size + 1): many tiles per CTA (tensor-memory accumulation across tiles), a ragged
+    last tile.  Both device kernels against the ORACLE's float64 autograd gradient of the reference loss on the same
+    rows (the CPU needs ~1 s for it), next to torch-float32's own distance from that truth.
+    Bar: 2e-6 of the largest gradient component (achieved: tcgen05 7.6e-7, fp32-FMA 3.6e-7, torch-float32 itself 3.6e-6;
+    north_star asks for 1e-5), achieved errors printed."""
     g = golden("learn_discrete")
     O, A, N = 4, 2, 65537
     rng = np.random.default_rng(12)
+    s_np = rng.uniform(-1, 1, (N, O)).astype(np.float32); a_np = rng.integers(0, A, (N, 1)).astype(np.float32)
     params = dev(g["init_flat"])
-    s = dev(rng.uniform(-1, 1, (N, O)).astype(np.float32)); a = dev(rng.integers(0, A, (N, 1)).astype(np.float32))
+    s = dev(s_np); a = dev(a_np)
     logp, _, _ = ops.policy_evaluate(params, False, O, A, s, a)
-    old_lp = logp + dev(rng.normal(0, 0.1, N).astype(np.float32))
-    adv = dev(rng.standard_normal(N).astype(np.float32)); ret = dev(rng.standard_normal(N).astype(np.float32))
-    out = {}
+    old_np = logp.cpu().numpy() + rng.normal(0, 0.1, N).astype(np.float32)
+    adv_np = rng.standard_normal(N).astype(np.float32); ret_np = rng.standard_normal(N).astype(np.float32)
+    keys = oppo.param_keys(False)
+
+    def oracle_grad(dtype):
+        p = {k: v.to(dtype).requires_grad_(True) for k, v in oppo.unflatten(g["init_flat"], False, O, A).items()}
+        c = lambda x: t.from_numpy(np.asarray(x)).to(dtype)  # noqa: E731
+        lo = oppo.ppo_loss(p, False, c(s_np), c(a_np[:, 0]), c(old_np), c(adv_np), c(ret_np), 0.2)
+        return float(lo.detach()), t.cat([x.reshape(-1) for x in t.autograd.grad(lo, [p[k] for k in keys])]).double().numpy()
+
+    lo, want = oracle_grad(t.float64)
+    _, want32 = oracle_grad(t.float32)
+    scale = np.abs(want).max()
+    err32 = np.abs(want32 - want).max() / scale
+    errs = {}
     for path in ("tc", "fp32"):
         grad = t.full_like(params, float("nan")); loss = t.zeros(4, dtype=t.float64, device="cuda")
         if path == "tc":
             ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
-            ops.ppo_grad_tc(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
+            ops.ppo_grad_tc(params, False, O, A, s, a, dev(old_np), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
             assert ops.ppo_grad_tc_status(ws) == 0
         else:
             ws = t.empty(ops.update_ws_floats(False, O, A, N), device="cuda")
-            ops.ppo_grad(params, False, O, A, s, a, old_lp, adv, ret, 0.2, 1.0 / N, grad, loss, ws)
-        out[path] = (grad.cpu().numpy().astype(np.float64), loss.cpu().numpy())
-    gt, gf = out["tc"][0], out["fp32"][0]
-    assert np.isfinite(gt).all()
-    assert np.abs(gt - gf).max() <= 3e-5 * np.abs(gf).max(), (np.abs(gt - gf).max(), np.abs(gf).max())
-    np.testing.assert_allclose(out["tc"][1], out["fp32"][1], rtol=1e-6)
+            ops.ppo_grad(params, False, O, A, s, a, dev(old_np), dev(adv_np), dev(ret_np), 0.2, 1.0 / N, grad, loss, ws)
+        got = grad.cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all()
+        l = loss.cpu().numpy()
+        lerr = abs((l[0] + 0.5 * l[1] - 0.01 * l[2]) / N - lo) / abs(lo)
+        errs[path] = (np.abs(got - want).max() / scale, lerr)
+    with capsys.disabled():
+        print(f"\n[parity] 65 537-row gradient vs float64 oracle autograd, max error / largest component: tcgen05 {errs['tc'][0]:.2e}, "
+              f"fp32-FMA {errs['fp32'][0]:.2e}, torch-float32 autograd {err32:.2e}; loss rel. error: tcgen05 {errs['tc'][1]:.1e}, fp32-FMA {errs['fp32'][1]:.1e}")
+    for path, (e, le) in errs.items():
+        assert e <= 2e-6 and le <= 1e-6, (path, e, le, err32)
 
 
 def test_rnd_intrinsic_and_grad_match_reference(ops, golden):

@@ -148,6 +148,35 @@ def test_gae_without_terminal_done_bootstraps_last_value():
     assert np.array_equal(bits(a), bits(b))
 
 
+def test_oracle_learn_schedule_and_float64_modes(golden):
+    """oracle.ppo.learn(schedule=...) with the reference's own sequential chunks spelled out as index lists reproduces the
+    default run bit for bit (and therefore the reference's post-update weights), a different schedule gives different
+    weights, and dtype=float64 evaluates the same update in double precision close to the float32 run."""
+    t.set_num_threads(1)
+    g, r = golden("learn_discrete"), golden("rollout_cartpole")
+    mem = {k: r[k] for k in ("states", "actions", "rewards", "dones")}
+    kw = dict(lr=float(g["lr"]), k_epochs=int(g["k_epochs"]), policy_clip=float(g["policy_clip"]), gae_lambda=float(g["GAE_lambda"]),
+              gamma=float(g["gamma"]), mini_batch_size=int(g["mini_batch_size"]))
+    N, mb = len(r["states"]), int(g["mini_batch_size"])
+    a = oppo.unflatten(g["init_flat"], False, 4, 2); oppo.learn(a, False, mem, **kw)
+    b = oppo.unflatten(g["init_flat"], False, 4, 2)
+    oppo.learn(b, False, mem, schedule=[np.arange(i, min(i + mb, N)) for i in range(0, N, mb)], **kw)
+    assert np.array_equal(bits(oppo.flatten(a, False).numpy()), bits(oppo.flatten(b, False).numpy()))
+    c = oppo.unflatten(g["init_flat"], False, 4, 2)
+    half = mb // 2   # two "ranks" of N/2 rows each: minibatch k = union of each rank's k-th chunk of mb/2 rows (SURVEY H7)
+    n0 = N // 2
+    sched = []
+    for k in range(-(-max(n0, N - n0) // half)):
+        sched.append(np.concatenate([np.arange(min(k * half, n0), min((k + 1) * half, n0)), n0 + np.arange(min(k * half, N - n0), min((k + 1) * half, N - n0))]))
+    assert sorted(np.concatenate(sched).tolist()) == list(range(N))
+    oppo.learn(c, False, mem, schedule=sched, **kw)
+    assert not np.array_equal(oppo.flatten(a, False).numpy(), oppo.flatten(c, False).numpy())
+    d = {k: v.double() for k, v in oppo.unflatten(g["init_flat"], False, 4, 2).items()}
+    oppo.learn(d, False, mem, dtype=t.float64, **kw)
+    w64 = oppo.flatten(d, False).numpy()
+    assert w64.dtype == np.float64 and np.abs(w64 - g["post_flat"]).max() < 3e-5
+
+
 def test_reference_float32_update_is_conditioned_at_1e5(golden):
     """How well-determined ARE the reference's post-update weights?  Re-run the reference's update loop (continuous
     fixture, 15 AdamW steps) in float64 on the same inputs: the reference's own float32 weights sit up to ~8e-6 away,
