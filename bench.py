@@ -40,19 +40,49 @@ FLOPS_PER_SAMPLE_EPOCH = 51_840.0
 EXECUTED_BF16_FLOPS_PER_ROW = (2 * 24 * 128 * 64 * 16 * 2 + 2 * 24 * 128 * 64 * 16 * 2 + 2 * 32 * 128 * 64 * 16 * 2 + 32 * 128 * 16 * 16 * 2) / 128.0
 
 
+# BASELINE.json `configs`, in its order (c1 = configs[0] ... c4 = configs[3]; configs[4], the size sweep, is the `configs.c5_*`
+# block of the c2 line).  `envs` / `mini_batch` are per GPU (weak scaling); `ref_envs` = the env count the CPU reference arm
+# really runs per step (a bounded sample; c1 is small enough to run whole).
+CONFIGS = {
+    "c1": dict(env_id="CartPole-v1", envs=32, horizon=500, k_epochs=11, mini_batch=512, batch=1024, ref_envs=32,
+               ppo=dict(is_continuous=False, observ_dim=4, action_dim=2),
+               note="README quick start (README.md:27-50): 32 envs, gymnasium's default 500-step TimeLimit, batch 1024 / mini 512"),
+    "c2": dict(env_id="CartPole-v1", envs=65536, horizon=128, k_epochs=11, mini_batch=65536, batch=1024, ref_envs=512,
+               ppo=dict(is_continuous=False, observ_dim=4, action_dim=2), note="the configuration the metric is quoted on"),
+    "c3": dict(env_id="Pendulum-v1", envs=262144, horizon=200, k_epochs=11, mini_batch=262144, batch=1024, ref_envs=256,
+               ppo=dict(is_continuous=True, observ_dim=3, action_dim=1, action_scaling=2.0),
+               note="tanh-Gaussian policy, gymnasium's 200-step TimeLimit"),
+    "c4": dict(env_id="Acrobot-v1", envs=65536, horizon=128, k_epochs=11, mini_batch=65536, batch=1024, ref_envs=512,
+               ppo=dict(is_continuous=False, observ_dim=6, action_dim=3, use_RND=True, beta=0.001),
+               note="RND predictor / target MLPs in the path"),
+}
+STATE_BOX = {"CartPole-v1": ([-0.05] * 4, [0.05] * 4), "Pendulum-v1": ([-3.141592653589793, -1.0], [3.141592653589793, 1.0]),
+             "Acrobot-v1": ([-0.1] * 4, [0.1] * 4), "MountainCar-v0": ([-0.6, 0.0], [-0.4, 0.0])}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--horizon", type=int, default=128)
-    ap.add_argument("--k-epochs", type=int, default=11)
-    ap.add_argument("--mini-batch", type=int, default=65536, help="minibatch rows per GPU")
-    ap.add_argument("--cpu-sample-envs", type=int, default=4096)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[i-1]")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the config's)")
+    ap.add_argument("--horizon", type=int, default=None)
+    ap.add_argument("--k-epochs", type=int, default=None)
+    ap.add_argument("--mini-batch", type=int, default=None, help="minibatch rows per GPU")
+    ap.add_argument("--cpu-sample-envs", type=int, default=None, help="envs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the `configs` block (c1, c3, c4, the c5 sweep, the ragged regime)")
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.envs = a.envs or c["envs"]
+    a.horizon = a.horizon or c["horizon"]
+    a.k_epochs = a.k_epochs or c["k_epochs"]
+    a.mini_batch = a.mini_batch or c["mini_batch"]
+    a.cpu_sample_envs = a.cpu_sample_envs or c["ref_envs"]
+    a.cfg = dict(c, envs=a.envs, horizon=a.horizon, k_epochs=a.k_epochs, mini_batch=a.mini_batch, ref_envs=a.cpu_sample_envs, name=a.config)
+    return a
 
 
 def peaks():
@@ -116,30 +146,57 @@ def cpu_port_steps(envs: int, horizon: int, k_epochs: int, mini_batch: int, n_st
     return total_steps, total_s
 
 
+def cpu_reference(cfg, envs: int, n_steps: int, warmup: int, threads: int):
+    """The CPU arm on `envs` envs of config `cfg`: the UNMODIFIED reference (oracle/_ref/reference, staged by build();
+    kind "reference") in a CPU-only child process, else - where nothing is staged - the oracle port (kind "port", CartPole only).
+    Returns (env steps, seconds, kind, note)."""
+    from oracle import ref_runner, stage_reference
+
+    if stage_reference.staged():
+        ppo = dict(cfg["ppo"], lr=1e-3, k_epochs=cfg["k_epochs"], batch_size=cfg["batch"], mini_batch_size=cfg["mini_batch"])
+        r = ref_runner.run_subprocess(dict(env_id=cfg["env_id"], envs=envs, horizon=cfg["horizon"], steps=n_steps, warmup=warmup,
+                                           threads=threads, ppo=ppo))
+        return r["env_steps"], r["seconds"], "reference", ("the unmodified reference (AsyncPPO.worker + PPO.learn, torch " + r["torch"] +
+                                                           " on the CPU); physics: " + r["physics"])
+    if cfg["env_id"] != "CartPole-v1":
+        raise SystemExit("the reference is not staged (run build() where /root/reference exists) and the port arm covers CartPole only")
+    steps, secs = cpu_port_steps(envs, cfg["horizon"], cfg["k_epochs"], cfg["mini_batch"], n_steps, warmup, threads)
+    return steps, secs, "port", "oracle/ restatement of the reference's Python path"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps, secs = cpu_port_steps(args.cpu_sample_envs, args.horizon, args.k_epochs, args.mini_batch, args.steps, args.warmup, threads)
+    cfg = args.cfg
+    steps, secs, kind, note = cpu_reference(cfg, args.cpu_sample_envs, args.steps, args.warmup, threads)
     v = steps / secs
-    sample = f"{args.cpu_sample_envs} of {args.envs} envs per step, same T={args.horizon}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}"
+    sample = (f"{args.cpu_sample_envs} envs per step (the B200 arm runs {args.envs} per GPU), same env, T={args.horizon}, k_epochs={args.k_epochs}, "
+              f"mini_batch={args.mini_batch}; {note}")
+    conf = workload_config(cfg, 1)
+    conf["num_envs_run_by_this_arm"] = args.cpu_sample_envs
+    conf["workload"] += f" [this CPU arm ran num_envs={args.cpu_sample_envs} per step: a bounded sample]" if args.cpu_sample_envs != args.envs else ""
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 networks / f64 physics", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": conf,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(args, world):
-    return {"workload": f"CartPole-v1 discrete, num_envs={args.envs}/GPU, one episode per env with TimeLimit T={args.horizon}, "
-                        f"PPO.learn k_epochs={args.k_epochs}, mini_batch_size={args.mini_batch}/GPU, batch_size=1024, lr=1e-3",
-            "num_envs_per_gpu": args.envs, "horizon": args.horizon, "k_epochs": args.k_epochs, "mini_batch_per_gpu": args.mini_batch,
+def workload_config(cfg, world):
+    p = cfg["ppo"]
+    kind = "continuous (tanh-Gaussian, action_scaling=%s)" % p.get("action_scaling") if p["is_continuous"] else "discrete"
+    return {"workload": f"{cfg['env_id']} {kind}{', use_RND beta=%s' % p['beta'] if p.get('use_RND') else ''}, num_envs={cfg['envs']}/GPU, one episode per env "
+                        f"with TimeLimit T={cfg['horizon']}, PPO.learn k_epochs={cfg['k_epochs']}, mini_batch_size={cfg['mini_batch']}/GPU, "
+                        f"batch_size={cfg['batch']}, lr=1e-3 (BASELINE configs[{int(cfg['name'][1]) - 1}]: {cfg['note']})",
+            "baseline_config": cfg["name"], "env_id": cfg["env_id"],
+            "num_envs_per_gpu": cfg["envs"], "horizon": cfg["horizon"], "k_epochs": cfg["k_epochs"], "mini_batch_per_gpu": cfg["mini_batch"],
             "parallelism": f"env-sharded dp{world}",
-            "l2": "256 MiB buffer rewritten between steps inside the timed region (L2 flush); the [T][C][E] rollout buffer alone is 235 MB > 126 MB L2"}
+            "l2": "256 MiB buffer rewritten between steps inside the timed region (L2 flush); at c2 the [T][C][E] rollout buffer alone is 235 MB > 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -182,13 +239,123 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------- B200 arm
+class Runner:
+    """One configuration through the drop-in API: AsyncPPO.worker() + PPO.learn() per step."""
+
+    def __init__(self, cfg, comm, dev, flush, fresh_policy_every_step=False):
+        import numpy as np
+        import torch as t
+
+        import prl_b200
+        from AsyncTools.AsyncPPO import AsyncPPO
+        from PPO import PPO
+
+        self.t, self.cfg, self.comm, self.dev, self.flush = t, cfg, comm, dev, flush
+        rank = comm.rank if comm else 0
+        world = comm.world_size if comm else 1
+        E = cfg["envs"]
+        t.manual_seed(0)  # identical initial weights and sampling seed on every rank
+        self.ppo = ppo = PPO(lr=1e-3, k_epochs=cfg["k_epochs"], batch_size=cfg["batch"], mini_batch_size=cfg["mini_batch"] * world, **cfg["ppo"])
+        ppo.show_progress = False
+        ppo.use_cuda_graph = True   # one captured epoch replayed k_epochs times (see PPO.learn)
+        ppo.graph_collectives = os.environ.get("PRL_GRAPH_COLLECTIVES", "1") == "1"   # NCCL allreduce captured in the graph too
+        # sharded runs: gradient exchange over NVLink peer memory inside the step kernel (0 = NCCL allreduce between grad and AdamW)
+        ppo.peer_exchange = os.environ.get("PRL_PEER_EXCHANGE", "1") == "1"
+        # (sharded: PPO broadcasts rank 0's replica at construction and keys the sampling / reset streams by rank - prl_b200.dist.rank_seed)
+        self.ap = AsyncPPO(env=prl_b200.make(cfg["env_id"], max_episode_steps=cfg["horizon"]), ppo=ppo, num_envs=E, steps=1)
+        lo, hi = STATE_BOX[cfg["env_id"]]
+        rng = np.random.default_rng(1234 + rank)
+        self.host_states = t.from_numpy(rng.uniform(lo, hi, (E, len(lo)))).pin_memory()       # e2e: start states from the host
+        self.host_weights = t.empty(ppo.policy.flat.numel(), dtype=t.float32).pin_memory()   # e2e: results read back
+        self.host_scores = t.empty(2, dtype=t.float64).pin_memory()
+        # ragged regime: every step starts from the freshly initialised policy (short, unequal episodes: the shrinking-batch path)
+        self.fresh = None
+        if fresh_policy_every_step:
+            o = ppo.optimizer
+            self.fresh = [(x, x.clone()) for x in (ppo.policy.flat, ppo.policy_old.flat, o.exp_avg, o.exp_avg_sq, o.step_dev)]
+            self.fresh_count = o.step_count
+
+    def step(self, e2e: bool):
+        t, ap, ppo = self.t, self.ap, self.ppo
+        if self.fresh is not None:
+            for dst, src in self.fresh:
+                dst.copy_(src)
+            ppo.optimizer.step_count = self.fresh_count
+        ap.step_score = 0
+        ap.reward_score = 0
+        ap.worker(initial_states=self.host_states if e2e else None)
+        n = int(ap.step_score)
+        ppo.learn()
+        if e2e:
+            self.host_weights.copy_(ppo.policy.flat, non_blocking=True)
+            self.host_scores.copy_(ap._scores, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+        self.flush.fill_(1)
+        return n
+
+    def timed(self, e2e: bool, k: int, profile: bool = False):
+        from prl_b200 import _lib
+
+        t, comm = self.t, self.comm
+        if comm:
+            comm.barrier()
+        t.cuda.synchronize()
+        counts0 = dict(_lib.CALL_COUNTS)
+        if profile:
+            _lib.profile_calls(True)
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        n = sum(self.step(e2e) for _ in range(k))
+        e1.record()
+        t.cuda.synchronize()
+        w1 = time.time()
+        prof = _lib.profile_calls(False) if profile else None
+        ms = t.tensor([e0.elapsed_time(e1)], dtype=t.float64, device=self.dev)
+        tot = t.tensor([float(n)], dtype=t.float64, device=self.dev)
+        if comm:
+            comm.allreduce_max_(ms)
+            comm.allreduce_(tot)
+            comm.barrier()
+        counts = {k_: v - counts0.get(k_, 0) for k_, v in _lib.CALL_COUNTS.items() if v - counts0.get(k_, 0)}
+        return float(tot.item()), float(ms.item()), counts, prof, (w0, w1)
+
+    def e2e_bytes(self):
+        return int(self.host_states.numel() * 8), int(self.host_weights.numel() * 4 + 16 + 16)
+
+    def close(self):
+        self.ppo.close()
+        self.ap.buffer = None
+        self.ap = self.ppo = None
+        import gc
+
+        gc.collect()
+        self.t.cuda.empty_cache()
+
+
+def short_line(cfg, comm, dev, flush, steps, warmup, fresh=False):
+    """One more configuration, measured like the headline (device-resident `value` + host-to-host `e2e`), in short form."""
+    world = comm.world_size if comm else 1
+    r = Runner(cfg, comm, dev, flush, fresh_policy_every_step=fresh)
+    for _ in range(warmup):
+        r.step(False)
+    r.step(True)
+    n_dev, ms_dev, counts, _, _ = r.timed(False, steps)
+    n_e2e, ms_e2e, _, _, _ = r.timed(True, steps)
+    h2d, d2h = r.e2e_bytes()
+    from prl_b200 import _lib
+
+    out = {"value": n_dev / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev / steps, "env_steps_per_step": n_dev / steps, "steps": steps, "warmup": warmup,
+           "n_gpus": world, "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": _lib.launches(counts), "update_path": r.ppo.update_path, "config": workload_config(cfg, world)}
+    r.close()
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch as t
 
-    import prl_b200
-    from AsyncTools.AsyncPPO import AsyncPPO
-    from PPO import PPO
     from prl_b200 import _lib
     from prl_b200 import dist as pdist
 
@@ -202,59 +369,13 @@ def run_b200(args):
     dev = t.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     t.cuda.set_device(dev)
 
+    cfg = args.cfg
     E, T = args.envs, args.horizon
-    t.manual_seed(0)  # identical initial weights and sampling seed on every rank
-    ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=1e-3, k_epochs=args.k_epochs, batch_size=1024,
-              mini_batch_size=args.mini_batch * world)
-    ppo.show_progress = False
-    ppo.use_cuda_graph = True   # one captured epoch replayed k_epochs times (see PPO.learn)
-    ppo.graph_collectives = os.environ.get("PRL_GRAPH_COLLECTIVES", "1") == "1"   # NCCL allreduce captured in the graph too
-    # sharded runs: gradient exchange over NVLink peer memory inside the step kernel (0 = NCCL allreduce between grad and AdamW)
-    ppo.peer_exchange = os.environ.get("PRL_PEER_EXCHANGE", "1") == "1"
-    # (sharded: PPO broadcasts rank 0's replica at construction and keys the sampling / reset streams by rank - prl_b200.dist.rank_seed)
-    ap = AsyncPPO(env=prl_b200.make("CartPole-v1", max_episode_steps=T), ppo=ppo, num_envs=E, steps=1)
     flush = t.empty(256 << 20, dtype=t.uint8, device=dev)
-    rng = np.random.default_rng(1234 + rank)
-    host_states = t.from_numpy(rng.uniform(-0.05, 0.05, (E, 4))).pin_memory()       # e2e: start states from the host
-    host_weights = t.empty(ppo.policy.flat.numel(), dtype=t.float32).pin_memory()   # e2e: results read back
-    host_scores = t.empty(2, dtype=t.float64).pin_memory()
-
-    def step(e2e: bool):
-        ap.step_score = 0
-        ap.reward_score = 0
-        ap.worker(initial_states=host_states if e2e else None)
-        n = int(ap.step_score)
-        ppo.learn()
-        if e2e:
-            host_weights.copy_(ppo.policy.flat, non_blocking=True)
-            host_scores.copy_(ap._scores, non_blocking=True)
-            t.cuda.current_stream().synchronize()
-        flush.fill_(1)
-        return n
-
-    def timed(e2e: bool, k: int, profile: bool):
-        if comm:
-            comm.barrier()
-        t.cuda.synchronize()
-        counts0 = dict(_lib.CALL_COUNTS)
-        if profile:
-            _lib.profile_calls(True)
-        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        e0.record()
-        n = sum(step(e2e) for _ in range(k))
-        e1.record()
-        t.cuda.synchronize()
-        w1 = time.time()
-        prof = _lib.profile_calls(False) if profile else None
-        ms = t.tensor([e0.elapsed_time(e1)], dtype=t.float64, device=dev)
-        tot = t.tensor([float(n)], dtype=t.float64, device=dev)
-        if comm:
-            comm.allreduce_max_(ms)
-            comm.allreduce_(tot)
-            comm.barrier()
-        counts = {k_: v - counts0.get(k_, 0) for k_, v in _lib.CALL_COUNTS.items() if v - counts0.get(k_, 0)}
-        return float(tot.item()), float(ms.item()), counts, prof, (w0, w1)
+    run = Runner(cfg, comm, dev, flush)
+    ppo, ap = run.ppo, run.ap
+    step, timed = run.step, run.timed
+    host_states, host_weights = run.host_states, run.host_weights
 
     # sharded parity, visible to the driver on every scaling run: ONE rollout consumed twice from the same replica state - by the
     # in-kernel peer-memory exchange (the timed path) and by the NCCL-allreduce path - must give the same weights (bit-identical
@@ -317,7 +438,10 @@ def run_b200(args):
     if gk is not None:
         g = per[gk]
         rows_epochs = n_prof / world * args.k_epochs           # sample-epochs this rank pushed through the update kernel
-        tf = rows_epochs * FLOPS_PER_SAMPLE_EPOCH / (g["ms"] * 1e-3) / 1e12
+        pp = cfg["ppo"]
+        heads_out = 2 * pp["action_dim"] if pp["is_continuous"] else pp["action_dim"]
+        flops_row = 3.0 * 2 * (pp["observ_dim"] * 64 + 2 * 64 * 64 + 64 * heads_out + 64)   # = 51 840 at CartPole shapes
+        tf = rows_epochs * flops_row / (g["ms"] * 1e-3) / 1e12
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")   # dram__bytes_read + write of one launch (ncu --set full capture)
         if os.path.exists(tpath):
@@ -328,11 +452,11 @@ def run_b200(args):
                 "traffic_unit": "bytes per launch (65 536 rows: 2.1 MB of row inputs + 36 KB of parameters are the algorithmic bytes)",
                 "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
-                "algorithmic_flops_per_sample_epoch": FLOPS_PER_SAMPLE_EPOCH, "avg_launch_ms": g["ms"] / g["calls"],
+                "algorithmic_flops_per_sample_epoch": flops_row, "avg_launch_ms": g["ms"] / g["calls"],
                 # what the tensor pipe really executes: every fp32-grade product is six bf16 MMAs (bf16x3 split) and the weight
                 # gradients run on stacked piece windows - 44.0 MFLOP of bf16 MMAs per 128-row tile
                 "executed_bf16_flops_per_sample_epoch": EXECUTED_BF16_FLOPS_PER_ROW,
-                "executed_bf16_tflops": tf * EXECUTED_BF16_FLOPS_PER_ROW / FLOPS_PER_SAMPLE_EPOCH,
+                "executed_bf16_tflops": tf * EXECUTED_BF16_FLOPS_PER_ROW / flops_row if gk != "prl_ppo_grad" else None,
                 "limiter": "CUDA-core epilogues (GroupNorm / SiLU / loss forward + backward, bf16x3 splitting, column sums): ncu issue slots 32 % "
                            "busy with 4.25 warps per scheduler, tensor pipe 9 % active, DRAM 0.3 % (profiles/r01_ncu_summary_v2.txt)",
                 "share_of_step": g["ms"] / ms_prof,
@@ -350,14 +474,12 @@ def run_b200(args):
         if name in per and per[name]["ms"] > 0:
             fma[name] = {"TFLOP/s_fp32": (n_prof / world) * fl / (per[name]["ms"] * 1e-3) / 1e12, "flops_per_row": fl, "ms": per[name]["ms"],
                          "fp32_fma_peak_TFLOP/s": 148 * 128 * 2 * 1.965e9 / 1e12}
-    micro = hbm_microbench(pk) if rank == 0 else None
-    if rank != 0:
-        return
+    micro = hbm_microbench(pk) if rank == 0 and cfg["env_id"] == "CartPole-v1" else None
     out = {
         "metric": METRIC, "value": n_dev / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 networks / f64 physics", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": workload_config(cfg, world),
         "env_steps_per_step": n_dev / args.steps,
         "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_states.numel() * 8),
                 "d2h_bytes_per_step": int(host_weights.numel() * 4 + 16 + 16), "ms_per_step": ms_e2e / args.steps},
@@ -372,13 +494,44 @@ def run_b200(args):
         "hbm_micro": micro,
         "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])},
     }
+    run.close()
+    del run, ppo, ap, step, timed
+    # ---- the other BASELINE configurations, measured the same way (short form), so that every config has a driver-visible number
+    extras = {}
+    if not args.no_extra_configs and args.config == "c2":
+        def sub(name, **kw):
+            return dict(CONFIGS[name], name=name, **kw)
+        plan = []
+        if world == 1:
+            plan += [("c1", sub("c1"), 30, 5, False), ("c3", sub("c3"), 2, 1, False), ("c4", sub("c4"), 3, 2, False),
+                     ("c2_ragged_fresh_policy", sub("c2", note="ragged regime: every step starts from the freshly initialised policy, so episodes "
+                                                               "are short and unequal (the shrinking-batch path, SURVEY H5)"), 5, 3, True)]
+        # configs[4]: CartPole sweep, envs per NODE = 2^16 .. 2^22 split over the GPUs of this run (2^16 per GPU = the headline line)
+        for lg in (18, 20, 22):
+            per_gpu = (1 << lg) // world
+            if per_gpu >= 65536 and per_gpu != E:
+                plan.append((f"c5_2^{lg}_envs_per_node", sub("c2", envs=per_gpu, note=f"configs[4] sweep point: 2^{lg} envs on {world} GPU(s)"), 2, 1, False))
+        for name, c, k, w, fresh in plan:
+            try:
+                extras[name] = short_line(c, comm, dev, flush, k, w, fresh)
+            except Exception as e:   # a failed extra must not lose the headline line
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    if rank != 0:
+        return
+    if extras:
+        out["configs"] = extras
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_cpu = 4 * args.cpu_sample_envs   # one untrained-policy step: ~20 env-steps per env, ~10 s of host work
-        cs, csec = cpu_port_steps(n_cpu, T, args.k_epochs, args.mini_batch, 1, 0, threads)
-        out["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"1 step of {n_cpu} of {E} envs, same T={T}, k_epochs={args.k_epochs}, mini_batch={args.mini_batch}; "
-                                         f"{cs} env-steps in {csec:.1f} s"}
+        n_cpu = args.cpu_sample_envs
+        cs, csec, kind, note = cpu_reference(cfg, n_cpu, 1, 0, threads)
+        out["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": f"1 step (worker + learn) of {n_cpu} envs (the B200 arm: {E}), same env, T={T}, k_epochs={args.k_epochs}, "
+                                         f"mini_batch={args.mini_batch}; {cs} env-steps in {csec:.1f} s; {note}"}
+        if extras and "c1" in extras and "value" in extras["c1"]:
+            c1 = dict(CONFIGS["c1"], name="c1")
+            cs, csec, kind, note = cpu_reference(c1, c1["envs"], 6, 1, threads)
+            extras["c1"]["cpu_baseline"] = {"value": cs / csec, "unit": UNIT, "cores": threads, "kind": kind,
+                                            "sample": f"the whole configuration (32 envs), 6 steps after 1 warm-up; {cs} env-steps in {csec:.1f} s; {note}"}
     print(json.dumps(out), flush=True)
 
 

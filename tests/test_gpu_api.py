@@ -326,6 +326,49 @@ def test_reference_unittest_call_patterns(api):
     ev.step(actions=np.random.randint(0, 2, size=4))
 
 
+def test_reference_unittests_run_unmodified(api, capsys):
+    """SURVEY.md section 2, component 12: the reference's own unittests/ (test_PPO.py, test_utils.py, test_AsyncPPO.py),
+    byte-identical copies staged at build() time by oracle/stage_reference.py next to the drop-in packages, executed as they
+    are: each file puts its parent directory first on sys.path and imports `PPO` / `AsyncTools` from there - the B200 build.
+    `import gymnasium` is served by tests/stubs/gymnasium (the image has no gymnasium wheel) whose make() is prl_b200.make."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.join(root, "parallel-reinforcement-learning_b200", "unittests")
+    files = sorted(f for f in (os.listdir(staged) if os.path.isdir(staged) else []) if f.startswith("test_") and f.endswith(".py"))
+    if not files:
+        pytest.skip("the reference's unittests are not staged (build() stages them where /root/reference exists)")
+    assert files == ["test_AsyncPPO.py", "test_PPO.py", "test_utils.py"]
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "tests", "stubs"), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", *files], cwd=staged, env=env, capture_output=True,
+                       text=True, timeout=900)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+    with capsys.disabled():
+        print(f"\n[reference unittests, unmodified, against the B200 build] {tail}")
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail and "error" not in tail
+
+
+def test_memory_del_slice_clears_device_rows(api):
+    """`del memory.states[:]` (the reference's Memory.clear idiom, Memory.py:26-30) on rows that live on the device."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    ppo = P.PPO(is_continuous=False, observ_dim=4, action_dim=2)
+    ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=16), ppo=ppo, num_envs=8, steps=1)
+    ap.worker()
+    m = ppo.memory
+    n = len(m.states)
+    assert n >= 8 and len(m.dones) == n and m.states[0].shape == (4,) and float(m.dones[n - 1]) == 1.0 and m.actions[-1].shape == ()
+    del m.states[:]
+    assert len(m.states) == 0 and len(m.actions) == n
+    del m.actions[:], m.rewards[:], m.dones[:]
+    assert len(m.actions) == len(m.rewards) == len(m.dones) == 0 and m._dev_count == 0
+    ap.worker()
+    assert len(m.states) >= 8
+    m.verify_transfers()
+
+
 def test_async_ppo_run_trains_cartpole(api):
     """train.py's flow (reference train.py:8-36) at the unittest's size: 4 envs, 1000 steps - then a larger batch to see
     the mean episode length move (CartPole reward = episode length)."""

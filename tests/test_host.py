@@ -177,3 +177,15 @@ def test_np_rng_header_equals_numpy_on_the_host(tmp_path):
         bg = np.random.PCG64(np.random.SeedSequence(int(s)))
         assert np.array_equal(raw[i], bg.random_raw(draws)), int(s)
         assert np.array_equal(uni[i], np.random.Generator(bg).random(draws)), int(s)
+
+
+def test_staged_reference_files_are_unmodified():
+    """oracle/stage_reference.py copies the reference's PPO/, AsyncTools/ and unittests/ byte for byte (what the GPU box runs as
+    "the reference's own unittests" and "the verbatim reference arm" really is the reference)."""
+    import pytest
+
+    from oracle import stage_reference as sr
+
+    if not os.path.isdir(sr.REF):
+        pytest.skip("/root/reference is not present on this box")
+    assert sr.stage() and sr.verify() == []
