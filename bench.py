@@ -462,7 +462,9 @@ def run_b200(args):
                 "share_of_step": g["ms"] / ms_prof,
                 "measured_on": "one launch-by-launch step after the timed region (the timed region replays CUDA graphs)"}
     hbm = {}
-    bytes_per = {"prl_rollout": 102.0, "prl_gae": 16.0, "prl_adv_normalize": 10.0, "prl_buffer_transfer": 56.0 + 4.0 * E / max(n_prof / world, 1)}
+    # algorithmic bytes per transition (the fused worker adds two planes to the rollout and three fields to the transfer)
+    bytes_per = {"prl_rollout": 102.0, "prl_rollout_eval": 110.0, "prl_gae": 16.0, "prl_gae_columns": 16.0, "prl_adv_normalize": 10.0,
+                 "prl_buffer_transfer": 56.0 + 4.0 * E / max(n_prof / world, 1), "prl_buffer_transfer_ex": 80.0 + 4.0 * E / max(n_prof / world, 1)}
     for name, b in bytes_per.items():
         if name in per and per[name]["ms"] > 0:
             gbs = (n_prof / world) * b / (per[name]["ms"] * 1e-3) / 1e9
@@ -470,7 +472,7 @@ def run_b200(args):
 
     # the two forward-only kernels are bound by the fp32 FMA pipe, not by HBM: report their TFLOP/s
     fma = {}
-    for name, fl in (("prl_rollout", 8960.0), ("prl_policy_evaluate", 17280.0)):
+    for name, fl in (("prl_rollout", 8960.0), ("prl_rollout_eval", 17280.0), ("prl_policy_evaluate", 17280.0)):
         if name in per and per[name]["ms"] > 0:
             fma[name] = {"TFLOP/s_fp32": (n_prof / world) * fl / (per[name]["ms"] * 1e-3) / 1e12, "flops_per_row": fl, "ms": per[name]["ms"],
                          "fp32_fma_peak_TFLOP/s": 148 * 128 * 2 * 1.965e9 / 1e12}

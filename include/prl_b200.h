@@ -102,6 +102,15 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
                         float *mem_rewards, float *mem_dones, int64_t *total, void *ws, size_t ws_bytes,
                         void *stream);
 
+/* The same with up to 4 extra per-transition planes [T][E] -> flat [N] rows (host arrays of device pointers): what the fused
+ * worker produced besides the reference's four fields - the acting policy's log-prob and state value of every transition
+ * (prl_rollout_eval) and the GAE returns computed on the time-major buffer (prl_gae_columns) - travels with them. */
+int prl_buffer_transfer_ex(int E, int T_cap, int obs_dim, int act_width, const float *buf_states,
+                           const float *buf_actions, const float *buf_rewards, const float *buf_dones, int n_extra,
+                           const float *const *extra_planes, float *const *extra_rows, int32_t *lengths, int64_t base,
+                           int64_t capacity, float *mem_states, float *mem_actions, float *mem_rewards,
+                           float *mem_dones, int64_t *total, void *ws, size_t ws_bytes, void *stream);
+
 /* ---------------------------------------------------------------- PPO.get_action (PPO/PPO.py:82-96) */
 /* states [n][O] f32 -> sampled actions: discrete int64 [n] (Categorical(probs).sample()), continuous f32 [n][A]
  * (tanh(mu + std*eps) * action_scaling).  Randomness: Philox(seed; row id, call_index) where row id = row_ids[i] (the
@@ -125,6 +134,15 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
                 uint64_t episode, const void *tape, double *state, int32_t *elapsed, uint8_t *terminal,
                 float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones, int32_t *lengths,
                 double *scores, void *stream);
+
+/* prl_rollout + the old-policy evaluation of PPO.learn (PPO/PPO.py:134-154) taken where the network outputs already exist:
+ * buf_logp[t][e] = log-prob of the stored action, buf_values[t][e] = V(s_t), both under `params` - bit-identical to
+ * prl_policy_evaluate on the same rows (same forward, same epilogue arithmetic).  Both NULL = prl_rollout.  Discrete
+ * policies and continuous ones with action_dim == 1. */
+int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed,
+                     uint64_t episode, const void *tape, double *state, int32_t *elapsed, uint8_t *terminal,
+                     float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones, float *buf_logp,
+                     float *buf_values, int32_t *lengths, double *scores, void *stream);
 
 /* ---------------------------------------------------------------- PPO.compute_gae (PPO/PPO.py:107-120) */
 /* Flat reverse scan over the env-major buffer, float32, same operation order as the reference;

@@ -276,12 +276,20 @@ class AsyncPPO:
         aw = d.action_dim if d.is_continuous else 1
         buf = self.buffer.device(env.sim.max_steps, d.observ_dim, aw)
         self._scores.zero_()
-        ops.rollout(env.sim, buf, ppo.policy_old.flat, ppo._action_scale(), ppo._seed, env.episode, self._scores)
+        # the old-policy evaluation of PPO.learn (PPO.py:134-154) rides along: the acting policy IS policy_old, so the log-prob of
+        # the sampled action and V(s) are by-products of the step (bit-identical to the separate pass); without RND the rewards are
+        # final too, so the GAE returns are computed right here on the time-major planes (coalesced across envs)
+        fuse_eval = bool(getattr(ppo, "fuse_evaluation", False)) and not d.is_continuous
+        ops.rollout(env.sim, buf, ppo.policy_old.flat, ppo._action_scale(), ppo._seed, env.episode, self._scores, evaluate=fuse_eval)
+        with_returns = fuse_eval and not ppo.use_RND
+        if with_returns:
+            ops.gae_columns(buf.rewards, buf.dones, buf.values, buf.lengths, ppo.gamma, ppo.GAE_lambda, out=buf.returns)
         scores = self._scores.cpu().numpy()  # the one host sync of the rollout: reward sum, number of env steps
         n_new = int(scores[1])
         self.reward_score += scores[0]
         self.step_score += n_new
-        ppo.memory.append_from_rollout(buf, n_new, scalar_actions=not d.is_continuous)
+        ppo.memory.append_from_rollout(buf, n_new, scalar_actions=not d.is_continuous, eval_tag=ppo._eval_tag() if fuse_eval else None,
+                                       with_returns=with_returns)
 
     def _worker_stepwise(self, initial_states=None):
         """The reference's loop, one kernel set per time step, host numpy between the calls.  Draws the same random

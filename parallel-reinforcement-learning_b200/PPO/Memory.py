@@ -93,6 +93,13 @@ class Memory:
         self._overflow = None       # the rollout buffer's overflow flag of the last transfer
         self._dev_cleared = set()   # fields emptied one by one through `del field[:]`
         self._fields = {n: _Field(self, n) for n in FIELDS}
+        # per-row by-products of the fused worker (not part of the reference's Memory): log-prob and state value under the acting
+        # policy, GAE returns.  Valid for the first _eval_rows rows as long as _eval_tag (what they were computed from: the acting
+        # policy's version, gamma, lambda) still describes the PPO that consumes them - PPO.learn() checks and otherwise recomputes.
+        self._eval = {}
+        self._eval_rows = 0
+        self._eval_tag = None
+        self._eval_has_returns = False
 
     # list-like attributes, assignable like the reference's plain lists
     states = property(lambda s: s._fields["states"], lambda s, v: s._assign("states", v))
@@ -119,6 +126,14 @@ class Memory:
             f._host.clear()
         self._dev_count = 0
         self._dev_cleared.clear()
+        self._eval_rows, self._eval_tag = 0, None
+
+    def evaluated(self, n, tag):
+        """(logp, values, returns or None) of the first n rows if the fused worker produced them for exactly these rows under `tag`."""
+        if n and self._eval_rows == n == self._dev_count and self._eval_tag == tag and not self._dev_cleared:
+            e = self._eval
+            return e["logp"][:n], e["values"][:n], (e["returns"][:n] if self._eval_has_returns else None)
+        return None
 
     def verify_transfers(self):
         """Host-synchronising check that the device agrees with the host's bookkeeping: the transfer kernel's row total equals
@@ -147,6 +162,11 @@ class Memory:
         if self._dev and self._dev_count:
             for k in FIELDS:
                 new[k][: self._dev_count] = self._dev[k][: self._dev_count]
+        if self._eval:
+            old, self._eval = self._eval, {k: torch.empty(capacity, dtype=torch.float32, device=device) for k in ("logp", "values", "returns")}
+            if self._eval_rows:
+                for k in old:
+                    self._eval[k][: self._eval_rows] = old[k][: self._eval_rows]
         self._dev, self._dev_cap = new, capacity
         if self._total is None:
             self._total = torch.zeros(1, dtype=torch.int64, device=device)
@@ -169,6 +189,7 @@ class Memory:
         for f in self._fields.values():
             f._host.clear()
         self._dev_count = nh
+        self._eval_rows, self._eval_tag = 0, None
 
     def device_view(self, obs_dim, act_width, device):
         """(states [N][O], actions [N][AW], rewards [N], dones [N]) on the device, host items uploaded first."""
@@ -176,9 +197,11 @@ class Memory:
         n = self._dev_count
         return tuple(self._dev[k][:n] for k in FIELDS)
 
-    def append_from_rollout(self, buf, n_new, scalar_actions=True):
+    def append_from_rollout(self, buf, n_new, scalar_actions=True, eval_tag=None, with_returns=False):
         """utils.buffer_to_target_buffer_transfer (utils.py:45-50) on the device: the per-env episodes of the rollout
-        buffer are concatenated env-major, time-minor behind the rows already stored; the buffer is cleared."""
+        buffer are concatenated env-major, time-minor behind the rows already stored; the buffer is cleared.
+        eval_tag is not None: buf.logp / buf.values (and buf.returns when with_returns) hold the fused worker's by-products for these
+        transitions; they travel along and stay usable while every stored row has them under the same tag."""
         device = buf.lengths.device
         self._upload_host(buf.O, buf.AW, device)
         base = self._dev_count
@@ -188,6 +211,15 @@ class Memory:
         want = base + (full if full * (buf.O + buf.AW + 2) * 4 <= (4 << 30) else int(n_new))
         self.reserve(max(want, base + int(n_new)), buf.O, buf.AW, device)
         self._scalar_actions = scalar_actions
-        buf.transfer(self._dev["states"], self._dev["actions"], self._dev["rewards"], self._dev["dones"], base, self._total)
+        extra = ()
+        keep = eval_tag is not None and (base == 0 or (self._eval_rows == base and self._eval_tag == eval_tag and self._eval_has_returns == bool(with_returns)))
+        if keep:
+            if not self._eval or self._eval["logp"].numel() < self._dev_cap:
+                old, self._eval = self._eval, {k: torch.empty(self._dev_cap, dtype=torch.float32, device=device) for k in ("logp", "values", "returns")}
+                for k in old:
+                    self._eval[k][:base] = old[k][:base]
+            extra = [(buf.logp, self._eval["logp"]), (buf.values, self._eval["values"])] + ([(buf.returns, self._eval["returns"])] if with_returns else [])
+        buf.transfer(self._dev["states"], self._dev["actions"], self._dev["rewards"], self._dev["dones"], base, self._total, extra=extra)
+        self._eval_rows, self._eval_tag, self._eval_has_returns = (base + int(n_new), eval_tag, bool(with_returns)) if keep else (0, None, False)
         self._dev_count = base + int(n_new)
         self._expect_total, self._overflow = self._dev_count, buf.overflow

@@ -91,6 +91,9 @@ class PPO:
         self.fused_optimizer = True   # tensor path, single process: one launch per optimiser step (prl_ppo_step_tc)
         self.graph_collectives = False  # also capture the per-minibatch gradient allreduce (NCCL) in the epoch graph
         self.use_cuda_graph = False   # capture each epoch of learn() in a CUDA graph (single process, >= 16 optimiser steps)
+        # AsyncPPO's fused worker also records log-prob / value of every transition under the acting policy (and, without RND, the
+        # GAE returns): learn() then skips its old-policy pass - same bits, one pass over the rows less
+        self.fuse_evaluation = True
         self.update_path = "tensor" if ops.tc_supported(is_continuous, observ_dim, action_dim) else "fp32"
         self._ws_owner = None         # which update path's header lives in self._ws
         self._p2p_ok = None           # sharded: can the ranks exchange gradients over peer memory (agreed once, collectively)
@@ -124,6 +127,12 @@ class PPO:
         if self._xch is not None:
             self._xch.close()
             self._xch = None
+
+    def _eval_tag(self):
+        """What the fused worker's by-products (log-prob, value, returns) were computed from; learn() uses them only if this still
+        holds: the acting network's buffer and its in-place version counter (any load / copy / step bumps it), gamma, lambda."""
+        f = self.policy_old.flat
+        return (f.data_ptr(), f._version, float(self.gamma), float(self.GAE_lambda), bool(self.use_RND))
 
     # ------------------------------------------------------------------------------------------------ acting
     def _action_scale(self) -> float:
@@ -196,9 +205,15 @@ class PPO:
                               ent=t.zeros(1, dtype=t.float64, device=self.device), stats=t.zeros(4, dtype=t.float64, device=self.device))
         R = self._rows
 
-        # old-policy evaluation (PPO.py:134-154): row-independent, so one launch over all N rows
-        old_logp, old_values, _ = ops.policy_evaluate(self.policy_old.flat, cont, O, A, states, actions, entropy_sum=R["ent"],
-                                                      logp=R["logp"][:N], value=R["values"][:N])
+        # old-policy evaluation (PPO.py:134-154): taken from the fused worker when it recorded it for exactly these rows under the
+        # policy_old that is still in place; otherwise row-independent, so one launch over all N rows
+        pre = self.memory.evaluated(N, self._eval_tag()) if self.fuse_evaluation else None
+        if pre is not None:
+            old_logp, old_values, pre_returns = pre
+        else:
+            pre_returns = None
+            old_logp, old_values, _ = ops.policy_evaluate(self.policy_old.flat, cont, O, A, states, actions, entropy_sum=R["ent"],
+                                                          logp=R["logp"][:N], value=R["values"][:N])
 
         if self.use_RND:  # PPO.py:157-178: rewards + intrinsic, THEN one predictor pass over the same chunks
             rewards = self.rnd.intrinsic_reward_device(states, add_to=rewards, out=R["rewards"][:N])
@@ -212,7 +227,12 @@ class PPO:
         self.memory.clear()  # PPO.py:184 (the device rows stay valid until the next transfer)
 
         # next_value = V(last stored state), PPO.py:188
-        returns = ops.gae(rewards, dones, old_values, self.gamma, self.GAE_lambda, out=R["returns"][:N], ws=R["gae_ws"])
+        # (every episode of a worker() ends with done = 1, so the flat scan factorises over envs: the fused worker's column scan
+        # over the time-major planes gives the same bits - tests/test_gpu_kernels.py::test_full_size_c2_properties)
+        if pre_returns is not None:
+            returns = pre_returns
+        else:
+            returns = ops.gae(rewards, dones, old_values, self.gamma, self.GAE_lambda, out=R["returns"][:N], ws=R["gae_ws"])
         # advantages = returns - values; (adv - mean) / (std + 1e-8) over ALL rows of ALL ranks (PPO.py:198-199)
         stats = R["stats"].zero_()
         ops.adv_normalize(returns, old_values, stats=stats, phase=1)
@@ -277,36 +297,58 @@ class PPO:
             return hi - lo
 
         # (sharded runs capture the NCCL allreduce inside the graph as well when graph_collectives is set)
-        use_graph = self.use_cuda_graph and (comm is None or self.graph_collectives or p2p) and not self.report_loss and steps >= 16
+        use_graph = self.use_cuda_graph and (comm is None or self.graph_collectives or p2p) and not self.report_loss and steps >= 16 and n_mb >= 2
         pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
         if use_graph:
-            # one epoch = n_mb launch triples with fixed pointers: capture once, replay k_epochs times (no host work between
-            # the 3 * steps launches).  last_losses[k] then ACCUMULATES minibatch k's loss sums over the epochs.
-            self.last_losses = t.zeros(n_mb, 4, dtype=t.float64, device=self.device)
+            # one epoch = n_mb launch sets with fixed pointers: captured once, replayed k_epochs times (no host work between the
+            # launches); last_losses[k] then ACCUMULATES minibatch k's loss sums over the epochs.  The capture covers the first
+            # n_mb - 1 minibatches - full ones, the same launches whatever N is - and is KEPT across learn() calls (key: every
+            # pointer and size that went into it); the last minibatch, whose row count follows N, is launched eagerly after each
+            # replay.  In steady state learn() therefore captures nothing: the capture cost (~4 ms of host time for 128 launches)
+            # would otherwise sit exposed between the rollout and the first optimiser step.
+            full = n_mb - 1
+            spans = tuple((min(k * mb_local, N), min((k + 1) * mb_local, N), counts[k]) for k in range(full))
+            o = self.optimizer
+            key = (tuple(x.data_ptr() for x in (states, actions, old_logp, adv, returns, self.policy.flat, self._ws, self._grad, o.exp_avg,
+                                                o.exp_avg_sq, o.step_dev, o.grad_norm)),
+                   spans, bool(p2p), bool(fused), float(self.policy_clip), o.lr, o.weight_decay, o.max_norm, id(self._xch), comm is not None)
+            cache = self.__dict__.setdefault("_graph_cache", {})
+            entry = cache.get(key)
             first_step = self.optimizer.step_count
-            side = self._side_stream = getattr(self, "_side_stream", None) or t.cuda.Stream()
-            side.wait_stream(t.cuda.current_stream())
-            graph = t.cuda.CUDAGraph()
-            counts0 = dict(ops._lib.CALL_COUNTS)
-            with t.cuda.stream(side):
-                graph.capture_begin()   # (torch.cuda.graph() would also synchronise, collect garbage and empty the allocator cache)
-                try:
-                    for k in range(n_mb):
-                        minibatch_step(k, self.last_losses[k])
-                finally:
-                    graph.capture_end()
-            t.cuda.current_stream().wait_stream(side)
-            captured = {k: v - counts0.get(k, 0) for k, v in ops._lib.CALL_COUNTS.items() if v != counts0.get(k, 0)}
+            if entry is None:
+                losses = t.zeros(n_mb, 4, dtype=t.float64, device=self.device)
+                self.last_losses = losses
+                side = self._side_stream = getattr(self, "_side_stream", None) or t.cuda.Stream()
+                side.wait_stream(t.cuda.current_stream())
+                graph = t.cuda.CUDAGraph()
+                counts0 = dict(ops._lib.CALL_COUNTS)
+                with t.cuda.stream(side):
+                    graph.capture_begin()   # (torch.cuda.graph() would also synchronise, collect garbage and empty the allocator cache)
+                    try:
+                        for k in range(full):
+                            minibatch_step(k, losses[k])
+                    finally:
+                        graph.capture_end()
+                t.cuda.current_stream().wait_stream(side)
+                captured = {k: v - counts0.get(k, 0) for k, v in ops._lib.CALL_COUNTS.items() if v != counts0.get(k, 0)}
+                for k, v in captured.items():
+                    ops._lib.CALL_COUNTS[k] -= v          # the capture itself launched nothing
+                while len(cache) >= 4:
+                    cache.pop(next(iter(cache)))
+                entry = cache[key] = (graph, losses, captured)
+            graph, losses, captured = entry
+            self.last_losses = losses.zero_()
+            self.optimizer.step_count = first_step   # (minibatch_step counted during a capture)
             for _ in range(self.k_epochs):
-                graph.replay()   # AdamW's step number is device-resident, so every replay advances it
+                if full:
+                    graph.replay()   # AdamW's step number is device-resident, so every replay advances it
+                    for k, v in captured.items():
+                        ops._lib.CALL_COUNTS[k] += v
+                minibatch_step(n_mb - 1, losses[n_mb - 1])
                 if pbar is not None:
                     pbar.update(N)
-            # launch accounting: the capture itself launched nothing, every replay launched all captured kernels
-            for k, v in captured.items():
-                ops._lib.CALL_COUNTS[k] += (self.k_epochs - 1) * v
             self.optimizer.step_count = first_step + steps
-            graphs = graph
-            self._graphs = graphs  # keep alive until the replays have run
+            self._graphs = graph  # keep alive until the replays have run
         else:
             self.last_losses = t.zeros(steps, 4, dtype=t.float64, device=self.device)
             step = 0

@@ -9,6 +9,7 @@
 namespace prl {
 
 constexpr float F32_EPS = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (probs_to_logits clamp)
+constexpr float LOG_2PI = 1.8378770664093453f;
 
 // shared-memory image of the trunk and the first n_heads heads (acting needs the policy heads only; evaluation adds
 // the critic), hidden-layer matrices staged TRANSPOSED ([in][out]) for the axpy-form forward.

@@ -441,12 +441,17 @@ __global__ void __launch_bounds__(EV_THREADS, 2)
 k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, float action_scaling, uint64_t seed,
           uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
           uint8_t *__restrict__ terminal, float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
-          float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores) {
+          float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores, float *__restrict__ blp,
+          float *__restrict__ bv) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = TAPED ? TPB : EV_THREADS;
     EvSmem S{};
+    // blp != nullptr: the old-policy evaluation of PPO.learn (PPO.py:134-154: log-prob of the stored action and V(s) under the
+    // acting policy) is taken here, where the network outputs of the step already exist: the critic head joins the forward and two
+    // more [T][E] planes are written.  Same forward, same epilogue arithmetic as k_policy_evaluate: the same bits.
+    const bool with_eval = !TAPED && blp != nullptr;
     if constexpr (!TAPED) {
-        S = ev_layout(L, L.n_heads - 1);
+        S = ev_layout(L, with_eval ? L.n_heads : L.n_heads - 1);
         ev_stage_weights(smem, S, params, L);   // made visible by the first barrier of the step loop
     }
     __shared__ double red[32];
@@ -489,12 +494,27 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
                     const float mu = out[S.col[0]];
                     const float ls = out[S.col[1]];
                     const float sd = softplus_t(fminf(fmaxf(ls, -2.f), 2.f));
-                    a = tanhf(fmaf(sqrtf(sd * sd), nrm[0], mu)) * action_scaling;
+                    const float tril = sqrtf(sd * sd);
+                    a = tanhf(fmaf(tril, nrm[0], mu)) * action_scaling;
                     a_store = a;
+                    if (with_eval) {   // k_policy_evaluate's continuous epilogue at A = 1 (log-prob of the STORED action)
+                        const float zt = (a_store - mu) / tril;
+                        const float q = fmaf(zt, zt, 0.f), hld = 0.f + logf(tril);
+                        blp[(size_t)t * E + e] = -0.5f * (1 * LOG_2PI + q) - hld;
+                    }
                 } else {
                     a = ev_sample_categorical(out, ENV::A, u01f(r[0]), nullptr);
                     a_store = (float)a;
+                    if (with_eval) {
+                        // ev_sample_categorical left e_a / S in the scratch row; k_policy_evaluate's epilogue from there on
+                        float P = 0.f;
+#pragma unroll
+                        for (int k = 0; k < ENV::A; ++k) P += out[k];
+                        const float pa = out[a] / P;
+                        blp[(size_t)t * E + e] = logf(fminf(fmaxf(pa, F32_EPS), 1.0f - F32_EPS));
+                    }
                 }
+                if (with_eval) bv[(size_t)t * E + e] = out[S.col[L.n_heads - 1]];
             }
             double r64;
             const bool term = ENV::step(s, a, r64);
@@ -645,7 +665,17 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
                         const float *buf_rewards, const float *buf_dones, int32_t *lengths, int64_t base, int64_t capacity,
                         float *mem_states, float *mem_actions, float *mem_rewards, float *mem_dones, int64_t *total,
                         void *ws, size_t ws_bytes, void *stream) {
+    return prl_buffer_transfer_ex(E, T_cap, obs_dim, act_width, buf_states, buf_actions, buf_rewards, buf_dones, 0, nullptr, nullptr, lengths, base,
+                                  capacity, mem_states, mem_actions, mem_rewards, mem_dones, total, ws, ws_bytes, stream);
+}
+
+int prl_buffer_transfer_ex(int E, int T_cap, int obs_dim, int act_width, const float *buf_states, const float *buf_actions,
+                           const float *buf_rewards, const float *buf_dones, int n_extra, const float *const *extra_planes,
+                           float *const *extra_rows, int32_t *lengths, int64_t base, int64_t capacity, float *mem_states,
+                           float *mem_actions, float *mem_rewards, float *mem_dones, int64_t *total, void *ws, size_t ws_bytes,
+                           void *stream) {
     PRL_REQUIRE(E > 0 && T_cap > 0 && total && ws && ws_bytes >= prl_scan_ws_bytes(E), "prl_buffer_transfer: bad arguments / workspace");
+    PRL_REQUIRE(n_extra >= 0 && n_extra <= 4 && (n_extra == 0 || (extra_planes && extra_rows)), "prl_buffer_transfer_ex: 0..4 extra [T][E] planes");
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = cdiv(E, SCAN_TPB);
     int32_t *sums = static_cast<int32_t *>(ws);
@@ -654,8 +684,10 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
     k_len_offsets<<<nb, SCAN_TPB, 0, st>>>(lengths, E, sums, base, offsets, total);
     // pack the channels of the four fields into groups of <= 4 (a group of 4 aligned channels of one field is stored as float4)
     XferPlan plan{};
-    struct Field { const float *src; float *dst; int C; } fields[4] = {
+    struct Field { const float *src; float *dst; int C; } fields[8] = {
         {buf_states, mem_states, obs_dim}, {buf_actions, mem_actions, act_width}, {buf_rewards, mem_rewards, 1}, {buf_dones, mem_dones, 1}};
+    const int n_fields = 4 + n_extra;
+    for (int k = 0; k < n_extra; ++k) fields[4 + k] = Field{extra_planes[k], extra_rows[k], 1};
     bool fits = true;
     XferGroup cur{};
     auto flush = [&]() {
@@ -664,7 +696,8 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
         plan.g[plan.ngroups++] = cur;
         cur = XferGroup{};
     };
-    for (const Field &f : fields) {
+    for (int fi = 0; fi < n_fields; ++fi) {
+        const Field &f = fields[fi];
         PRL_REQUIRE(f.src && f.dst && f.C > 0, "prl_buffer_transfer: null field");
         int c = 0;
         if (f.C % 4 == 0 && ((uintptr_t)f.dst & 15) == 0) {
@@ -682,7 +715,7 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
         }
     }
     flush();
-    for (const Field &f : fields) fits = fits && ((uintptr_t)f.src & 15) == 0;
+    for (int fi = 0; fi < n_fields; ++fi) fits = fits && ((uintptr_t)fields[fi].src & 15) == 0;
     if (fits && E % 4 == 0) {
         const size_t smem = (size_t)XF_WARPS * 4 * 32 * 33 * sizeof(float);
         PRL_CUDA(cudaFuncSetAttribute(k_transfer_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -693,6 +726,7 @@ int prl_buffer_transfer(int E, int T_cap, int obs_dim, int act_width, const floa
         k_transfer<<<tb, 128, 0, st>>>(E, T_cap, act_width, buf_actions, lengths, offsets, mem_actions, capacity);
         k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_rewards, lengths, offsets, mem_rewards, capacity);
         k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, buf_dones, lengths, offsets, mem_dones, capacity);
+        for (int k = 0; k < n_extra; ++k) k_transfer<<<tb, 128, 0, st>>>(E, T_cap, 1, extra_planes[k], lengths, offsets, extra_rows[k], capacity);
     }
     k_zero_i32<<<cdiv(E, 256), 256, 0, st>>>(lengths, E);
     return check_launch("k_transfer");
@@ -715,22 +749,35 @@ int prl_policy_act(const float *params, int is_continuous, int obs_dim, int acti
 int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
                 const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
                 float *buf_rewards, float *buf_dones, int32_t *lengths, double *scores, void *stream) {
+    return prl_rollout_eval(env_id, E, T_cap, params, action_scaling, seed, episode, tape, state, elapsed, terminal, buf_states, buf_actions,
+                            buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, stream);
+}
+
+int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
+                     const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
+                     float *buf_rewards, float *buf_dones, float *buf_logp, float *buf_values, int32_t *lengths, double *scores,
+                     void *stream) {
     PRL_REQUIRE(E > 0 && T_cap > 0 && state && elapsed && terminal && buf_states && buf_actions && buf_rewards && buf_dones &&
                     lengths && scores, "prl_rollout: bad arguments");
     PRL_REQUIRE(tape || params, "prl_rollout: need policy parameters or an action tape");
+    PRL_REQUIRE((buf_logp == nullptr) == (buf_values == nullptr) && !(tape && buf_logp),
+                "prl_rollout_eval: buf_logp and buf_values go together and need the policy (no action tape)");
     return dispatch_env(env_id, [&](auto env) -> int {
         using ENV = decltype(env);
         cudaStream_t st = (cudaStream_t)stream;
         const PolicyLayout L = make_policy_layout(ENV::CONT, ENV::O, ENV::A);
         if (tape) {
             k_rollout<ENV, true><<<cdiv(E, TPB), TPB, 0, st>>>(E, T_cap, params, L, action_scaling, seed, episode, tape, state, elapsed,
-                                                              terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores);
+                                                              terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores,
+                                                              nullptr, nullptr);
         } else {
-            const size_t smem = (size_t)ev_layout(L, L.n_heads - 1).total * sizeof(float);
+            PRL_REQUIRE(!(buf_logp && ENV::CONT && ENV::A != 1), "prl_rollout_eval: continuous envs with action_dim > 1 are evaluated by prl_policy_evaluate");
+            const size_t smem = (size_t)ev_layout(L, buf_logp ? L.n_heads : L.n_heads - 1).total * sizeof(float);
+            PRL_REQUIRE(smem <= 227 * 1024, "prl_rollout_eval: %zu B of shared memory needed (> 227 KB)", smem);
             PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
                                                                  elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
-                                                                 lengths, scores);
+                                                                 lengths, scores, buf_logp, buf_values);
         }
         return check_launch("k_rollout");
     });

@@ -6,8 +6,6 @@
 
 namespace prl {
 
-constexpr float LOG_2PI = 1.8378770664093453f;
-
 // =============================================================================================== fused minibatch step
 constexpr int UP_NT = 256;          // rows per tile = threads per block
 constexpr int UP_NTP = UP_NT + 4;   // padded row stride of the [64][rows] staging arrays (keeps float4 alignment)

@@ -41,9 +41,12 @@ PROTOTYPES = {
     "prl_buffer_append": (_i32, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "prl_buffer_transfer": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _sz, _vp]),
+    "prl_buffer_transfer_ex": (_i32, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _sz, _vp]),
     "prl_policy_act": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "prl_policy_evaluate": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "prl_rollout": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_rollout_eval": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "prl_gae": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp, _sz, _vp]),
     "prl_gae_ws_bytes": (_sz, [_i64]),
     "prl_gae_columns": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _vp, _vp]),
@@ -107,7 +110,7 @@ def require_cuda():
 KERNELS_PER_CALL = {
     "prl_test_sincos": 1, "prl_test_pow2": 1, "prl_test_philox": 1, "prl_test_umma": 1, "prl_env_reset": 1, "prl_env_reset_numpy": 1, "prl_test_pcg64": 1, "prl_env_set_state": 1,
     "prl_env_get_state": 1, "prl_env_step": 1, "prl_compact_indices": 2, "prl_gather_rows": 1, "prl_mask_update": 1,
-    "prl_buffer_append": 1, "prl_buffer_transfer": 4, "prl_policy_act": 1, "prl_policy_evaluate": 1, "prl_rollout": 1,
+    "prl_buffer_append": 1, "prl_buffer_transfer": 4, "prl_buffer_transfer_ex": 4, "prl_policy_act": 1, "prl_policy_evaluate": 1, "prl_rollout": 1, "prl_rollout_eval": 1,
     "prl_gae": 1, "prl_gae_columns": 1, "prl_adv_normalize": 1, "prl_ppo_grad": 2, "prl_ppo_grad_tc": 2, "prl_ppo_step_tc": 1, "prl_ppo_step_tc_p2p": 1, "prl_adamw_step": 1, "prl_adamw_step_dev": 1,
     "prl_rnd_intrinsic": 1, "prl_rnd_grad": 2,
 }

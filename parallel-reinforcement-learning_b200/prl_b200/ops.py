@@ -186,6 +186,15 @@ class RolloutBuffer:
         self.lengths = torch.zeros(self.E, dtype=torch.int32, device=d)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
         self._ws = _ws(_lib.fn("prl_scan_ws_bytes")(self.E))
+        # what the fused worker can produce besides the reference's four fields (allocated by want_eval()): the acting policy's
+        # log-prob and state value of every transition, and the GAE returns computed on the time-major planes
+        self.logp = self.values = self.returns = None
+
+    def want_eval(self):
+        if self.logp is None:
+            d = _dev()
+            self.logp, self.values, self.returns = (torch.empty(self.T, self.E, dtype=torch.float32, device=d) for _ in range(3))
+        return self
 
     def append(self, active_idx, n, states, actions, rewards, dones):
         call("prl_buffer_append", self.E, self.T, n, _ptr(active_idx, torch.int32), _ptr(states, torch.float32), self.O,
@@ -193,12 +202,19 @@ class RolloutBuffer:
              _ptr(self.states), _ptr(self.actions), _ptr(self.rewards), _ptr(self.dones), _ptr(self.lengths),
              _ptr(self.overflow), _stream())
 
-    def transfer(self, mem_states, mem_actions, mem_rewards, mem_dones, base, total_out):
+    def transfer(self, mem_states, mem_actions, mem_rewards, mem_dones, base, total_out, extra=()):
+        """`extra`: (plane [T][E], rows [cap]) pairs that travel with the four fields (prl_buffer_transfer_ex)."""
         cap = mem_rewards.numel()
-        call("prl_buffer_transfer", self.E, self.T, self.O, self.AW, _ptr(self.states), _ptr(self.actions),
-             _ptr(self.rewards), _ptr(self.dones), _ptr(self.lengths), base, cap, _ptr(mem_states, torch.float32),
-             _ptr(mem_actions, torch.float32), _ptr(mem_rewards, torch.float32), _ptr(mem_dones, torch.float32),
-             _ptr(total_out, torch.int64), _ptr(self._ws), self._ws.numel(), _stream())
+        n = len(extra)
+        planes = (C.c_void_p * max(n, 1))(*[p.data_ptr() for p, _ in extra])
+        rows = (C.c_void_p * max(n, 1))(*[r.data_ptr() for _, r in extra])
+        for p, r in extra:
+            assert p.is_cuda and p.is_contiguous() and p.dtype == torch.float32 and tuple(p.shape) == (self.T, self.E)
+            assert r.is_cuda and r.is_contiguous() and r.dtype == torch.float32 and r.numel() >= cap
+        call("prl_buffer_transfer_ex", self.E, self.T, self.O, self.AW, _ptr(self.states), _ptr(self.actions),
+             _ptr(self.rewards), _ptr(self.dones), n, planes if n else None, rows if n else None, _ptr(self.lengths), base, cap,
+             _ptr(mem_states, torch.float32), _ptr(mem_actions, torch.float32), _ptr(mem_rewards, torch.float32),
+             _ptr(mem_dones, torch.float32), _ptr(total_out, torch.int64), _ptr(self._ws), self._ws.numel(), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ policy
@@ -224,11 +240,15 @@ def policy_evaluate(params, is_continuous, O, A, states, actions, entropy_sum=No
     return logp, value, entropy_sum
 
 
-def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, episode, scores, tape=None):
-    """Fused AsyncPPO.worker(): one launch.  scores: float64[2] device tensor, accumulated."""
-    call("prl_rollout", env.code, env.E, buf.T, _ptr(params), float(action_scaling or 1.0), seed, episode, _ptr(tape),
+def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, episode, scores, tape=None, evaluate=False):
+    """Fused AsyncPPO.worker(): one launch.  scores: float64[2] device tensor, accumulated.  evaluate: also fill buf.logp / buf.values
+    (the old-policy evaluation of PPO.learn, bit-identical to policy_evaluate on the same rows)."""
+    if evaluate:
+        buf.want_eval()
+    call("prl_rollout_eval", env.code, env.E, buf.T, _ptr(params), float(action_scaling or 1.0), seed, episode, _ptr(tape),
          _ptr(env.state), _ptr(env.elapsed), _ptr(env.terminal), _ptr(buf.states), _ptr(buf.actions), _ptr(buf.rewards),
-         _ptr(buf.dones), _ptr(buf.lengths), _ptr(scores, torch.float64), _stream())
+         _ptr(buf.dones), _ptr(buf.logp) if evaluate else None, _ptr(buf.values) if evaluate else None, _ptr(buf.lengths),
+         _ptr(scores, torch.float64), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ GAE

@@ -148,13 +148,16 @@ def test_learn_with_cuda_graph_epochs_is_bit_identical(api):
         ppo.show_progress = False
         ppo.use_cuda_graph = graph
         ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=64), ppo=ppo, num_envs=256, steps=1)
-        ap.worker()
-        assert len(ppo.memory.states) >= 4 * 512   # >= 4 minibatches x 5 epochs = 20 optimiser steps
-        ppo.learn()
+        for _ in range(4):   # later rounds reuse the captured epoch when the full minibatches are the same launches (the last,
+            ap.worker()      # partial one is launched eagerly) or capture a new one when their number changed
+            assert len(ppo.memory.states) >= 4 * 512   # >= 4 minibatches x 5 epochs = 20 optimiser steps
+            ppo.learn()
+        if graph:
+            assert 1 <= len(ppo._graph_cache) <= 4
         out.append((ppo.policy.flat.cpu().numpy(), ppo.optimizer.exp_avg_sq.cpu().numpy(), ppo.optimizer.step_count,
                     int(ppo.optimizer.step_dev[0].item())))
     assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(bits(out[0][1]), bits(out[1][1]))
-    assert out[0][2] == out[1][2] == out[0][3] == out[1][3] and out[0][2] >= 20
+    assert out[0][2] == out[1][2] == out[0][3] == out[1][3] and out[0][2] >= 80
 
 
 def test_fused_optimizer_step_matches_separate_kernels(api):
@@ -269,6 +272,59 @@ def test_fused_worker_equals_stepwise_worker(api, key, cont):
         assert np.array_equal(bits(f[i]), bits(s[i])), i
     assert f[5] == pytest.approx(s[5], rel=1e-5)
     assert (f[3].sum() == 2 * E)  # every episode ends with done = 1 (termination or truncation)
+
+
+@pytest.mark.parametrize("key,rnd", [("cartpole", False), ("acrobot", False), ("acrobot", True), ("mountaincar", False)])
+def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
+    """The fused worker records, per transition, the acting policy's log-prob and state value (prl_rollout_eval) and - without
+    RND - the GAE returns (prl_gae_columns on the time-major planes).  They must be the bits PPO.learn's own passes produce on
+    the transferred rows (PPO.py:134-154 old-policy evaluation, :107-120 compute_gae), and learn() must end with the same
+    weights whether it consumes them or recomputes them.  Also covers rows accumulated over two worker() calls."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    from prl_b200 import ops
+
+    def run(fuse):
+        t.manual_seed(11)
+        env = prl.make(ENVS[key], max_episode_steps=48)
+        ppo = P.PPO(is_continuous=False, observ_dim=env.observ_dim, action_dim=env.action_dim, k_epochs=2, batch_size=64, mini_batch_size=512,
+                    use_RND=rnd, beta=0.01)
+        ppo.show_progress = False
+        ppo.fuse_evaluation = fuse
+        ap = A.AsyncPPO.AsyncPPO(env=env, ppo=ppo, num_envs=300, steps=1)
+        ap.worker()
+        ap.worker()   # rows of a second call land behind the first one's
+        return ppo, ap
+
+    ppo, ap = run(True)
+    m = ppo.memory
+    N = m._dev_count
+    pre = m.evaluated(N, ppo._eval_tag())
+    assert pre is not None and N >= 600
+    states, actions, rewards, dones = m.device_view(ppo.observ_dim, 1, ppo.device)
+    logp, value, _ = ops.policy_evaluate(ppo.policy_old.flat, False, ppo.observ_dim, ppo.action_dim, states, actions)
+    assert np.array_equal(bits(pre[0].cpu().numpy()), bits(logp.cpu().numpy()))
+    assert np.array_equal(bits(pre[1].cpu().numpy()), bits(value.cpu().numpy()))
+    if rnd:
+        assert pre[2] is None     # the intrinsic reward is only known in learn(): GAE stays there
+    else:
+        ret = ops.gae(rewards, dones, value, ppo.gamma, ppo.GAE_lambda)
+        assert np.array_equal(bits(pre[2].cpu().numpy()), bits(ret.cpu().numpy()))
+        want = cref.gae(rewards.cpu().numpy(), dones.cpu().numpy(), value.cpu().numpy(), value.cpu().numpy()[-1], ppo.gamma, ppo.GAE_lambda)
+        assert np.array_equal(bits(pre[2].cpu().numpy()), bits(want))
+    # a policy_old that changed after the rollout invalidates them (learn() then evaluates again, like the reference)
+    ppo.policy_old.flat.mul_(1.0)
+    assert m.evaluated(N, ppo._eval_tag()) is None
+    # same final weights with and without the fused by-products
+    a, _ = run(True)
+    b, _ = run(False)
+    assert a.memory.evaluated(a.memory._dev_count, a._eval_tag()) is not None and b.memory.evaluated(b.memory._dev_count, b._eval_tag()) is None
+    calls0 = dict(ops._lib.CALL_COUNTS)
+    a.learn()
+    assert ops._lib.CALL_COUNTS.get("prl_policy_evaluate", 0) == calls0.get("prl_policy_evaluate", 0)   # the pass is really skipped
+    b.learn()
+    assert np.array_equal(bits(a.policy.flat.cpu().numpy()), bits(b.policy.flat.cpu().numpy()))
+    if rnd:
+        assert np.array_equal(bits(a.rnd.pred_flat.cpu().numpy()), bits(b.rnd.pred_flat.cpu().numpy()))
 
 
 def test_reference_unittest_call_patterns(api):
