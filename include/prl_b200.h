@@ -42,18 +42,6 @@ int64_t prl_policy_param_count(int is_continuous, int obs_dim, int action_dim);
 int64_t prl_rnd_param_count(int in_features, int out_features);
 size_t prl_scan_ws_bytes(int64_t n);
 
-/* ---------------------------------------------------------------- test hooks (parity tests only) */
-int prl_test_sincos(const double *x, double *sin_out, double *cos_out, int64_t n, void *stream);
-int prl_test_pow2(const double *x, double *out, const float *xf, float *outf, int64_t n, void *stream);
-/* out[i][k] = k-th 64-bit output of np.random.PCG64(np.random.SeedSequence(seeds[i])) */
-int prl_test_pcg64(const uint64_t *seeds, int n, int draws, uint64_t *out, void *stream);
-int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
-/* tensor-core building blocks (csrc/umma.cuh): one 128-row tile, tcgen05.mma kind::tf32 from shared memory.
- * mode 0: D[128][128] = A[128][64] B[128][64]^T; 1: D[128][64] = A[128][64] B[64:128][0:64]; 2: D[128][64] =
- * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[16]
- * (see csrc/umma_test.cu).  *status != 0: the MMA never completed. */
-int prl_test_umma(int mode, const float *A, const float *B, float *D, int *status, const int32_t *cfg_host, void *stream);
-
 /* ---------------------------------------------------------------- EnvVectorizer (AsyncTools/AsyncPPO.py:35-102) */
 /* reset(): AsyncPPO.py:48-62.  Draws every env's start state from Philox(seed, episode) in the env's reset box,
  * zeroes the TimeLimit counters and the terminal mask, writes obs [E][O] float32. */
@@ -138,11 +126,15 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
 /* prl_rollout + the old-policy evaluation of PPO.learn (PPO/PPO.py:134-154) taken where the network outputs already exist:
  * buf_logp[t][e] = log-prob of the stored action, buf_values[t][e] = V(s_t), both under `params` - bit-identical to
  * prl_policy_evaluate on the same rows (same forward, same epilogue arithmetic).  Both NULL = prl_rollout.  Discrete
- * policies and continuous ones with action_dim == 1. */
+ * policies and continuous ones with action_dim == 1.
+ * auto_reset_horizon > 0 (opt-in; 0 = the reference's worker, where a finished env drops out - AsyncPPO.py:118,143-146):
+ * an env whose episode ends - terminated, or auto_reset_horizon (= the TimeLimit) steps into the episode - is reset in
+ * place (its k-th reset draws what prl_env_reset draws in episode `episode | k << 40`) and keeps stepping, so every env
+ * fills all T_cap slots; the last slot closes the running episode with done = 1.  lengths[e] = T_cap. */
 int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed,
                      uint64_t episode, const void *tape, double *state, int32_t *elapsed, uint8_t *terminal,
                      float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones, float *buf_logp,
-                     float *buf_values, int32_t *lengths, double *scores, void *stream);
+                     float *buf_values, int32_t *lengths, double *scores, int auto_reset_horizon, void *stream);
 
 /* ---------------------------------------------------------------- PPO.compute_gae (PPO/PPO.py:107-120) */
 /* Flat reverse scan over the env-major buffer, float32, same operation order as the reference;
@@ -181,10 +173,14 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
                     float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
                     void *stream);
 int prl_ppo_grad_tc_status(const float *ws, int *status_host, void *stream);
-/* prl_ppo_grad_tc + clip_grad_norm_ + AdamW in ONE cooperative launch (single-GPU path): after the per-CTA partial
- * gradients are written, a grid barrier, a fixed-order reduction of each CTA's slice of the parameters, a second
- * barrier for the squared norm, then the AdamW update of `params` in place.  `grad` receives the reduced gradient,
- * step_counter is the 24-byte optimiser clock of prl_adamw_step_dev.  Status word 2 = a grid barrier timed out. */
+/* prl_ppo_grad_tc + clip_grad_norm_ + AdamW in ONE cooperative launch (single-GPU path), with no grid barrier: every CTA
+ * writes its partial-gradient row and loss sums and adds one to an arrival counter (release); every CTA waits for the
+ * counter to reach the grid size, reduces its 64-parameter slices over the CTAs' rows in a fixed order (bit-identical to
+ * the separate reduction of prl_ppo_grad_tc) and publishes the squared norm of its slices as a tagged 64-bit word
+ * {payload, launch number}; the leader CTA collects those and publishes the clip coefficient the same way; then every
+ * CTA applies clip_grad_norm_ + AdamW to its slices of `params` in place.  `grad` receives the reduced gradient,
+ * step_counter is the 24-byte optimiser clock of prl_adamw_step_dev.  Every wait is bounded in wall-clock time
+ * (PRL_TC_TIMEOUT_MS, default generous): status word 2 = a wait on another CTA timed out. */
 int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
                     const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
                     float policy_clip, float inv_count, float *grad, double *loss_out, float *exp_avg,
@@ -192,10 +188,13 @@ int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_di
                     double *grad_norm_out, float *ws, size_t ws_floats, void *stream);
 /* Sharded form of prl_ppo_step_tc: the gradient allreduce happens INSIDE the kernel over NVLink peer memory.  Every rank
  * owns an exchange buffer (prl_p2p_alloc of prl_p2p_exchange_bytes; shared with the other ranks of the node through CUDA
- * IPC handles: prl_p2p_get_handle / prl_p2p_open_handle); peer_bufs is a DEVICE array of `world` pointers to the ranks'
- * buffers (own one at [rank]).  Each rank writes its locally reduced gradient into its buffer, raises a flag on every
- * peer, and sums all ranks' buffers in rank order (bit-identical on every rank) before clip + AdamW.  b may be 0 (a rank
- * without rows in this minibatch still takes part).  Status word 3 = a peer never signalled. */
+ * IPC handles: prl_p2p_get_handle / prl_p2p_open_handle) = inbox[2 (step parity)][world (sender)][P] of 8-byte words
+ * {float bits, step number}; peer_bufs is a DEVICE array of `world` pointers to the ranks' buffers (own one at [rank]).
+ * After its slice reduction a CTA pushes every value of its slices, tagged with the optimiser step number, into all
+ * ranks' inboxes (one naturally aligned 64-bit store per value and rank: the tag cannot arrive without its value - no
+ * fence, no flag), polls the `world` words of each of its parameters in its own inbox until all carry this step's number
+ * and sums them in rank order (bit-identical on every rank); then squared norm, clip and AdamW as on one GPU.  b may be
+ * 0 (a rank without rows in this minibatch still takes part).  Status word 3 = a peer never signalled (bounded wait). */
 int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int action_dim, const float *states,
                         const float *actions, const float *old_logp, const float *adv, const float *returns, int64_t b,
                         float policy_clip, float inv_count, float *grad, double *loss_out, float *exp_avg,

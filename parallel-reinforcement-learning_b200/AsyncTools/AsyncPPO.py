@@ -246,6 +246,12 @@ class AsyncPPO:
 
         self.buffer = VecMemory(num_envs)
         self.fused = True           # set False to force the step-by-step loop (same results, one launch set per step)
+        # opt-in, NOT the reference's worker (where a finished env drops out until the next worker(), AsyncPPO.py:118,143-146): with
+        # auto_reset a finished env is reset inside the rollout kernel and keeps stepping, so every worker() yields exactly
+        # num_envs x rollout_steps transitions (rollout_steps defaults to the env's TimeLimit; the last slot closes the running
+        # episode with done = 1).  Fused worker only.
+        self.auto_reset = False
+        self.rollout_steps = None
         self.show_progress = True
         self._scores = t.zeros(2, dtype=t.float64, device=self.env.device)
 
@@ -264,6 +270,8 @@ class AsyncPPO:
         signature): host or device fp64 [E, S] start states to use instead of a random reset."""
         if self._can_fuse():
             self._worker_fused(initial_states)
+        elif self.auto_reset:
+            raise RuntimeError("auto_reset is an option of the fused worker (the reference's step-by-step loop has no auto-reset)")
         else:
             self._worker_stepwise(initial_states)
 
@@ -274,13 +282,17 @@ class AsyncPPO:
         else:
             env.reset_to_device(initial_states)
         aw = d.action_dim if d.is_continuous else 1
-        buf = self.buffer.device(env.sim.max_steps, d.observ_dim, aw)
+        T, horizon = env.sim.max_steps, 0
+        if self.auto_reset:
+            T, horizon = int(self.rollout_steps or env.sim.max_steps), env.sim.max_steps
+        buf = self.buffer.device(T, d.observ_dim, aw)
         self._scores.zero_()
         # the old-policy evaluation of PPO.learn (PPO.py:134-154) rides along: the acting policy IS policy_old, so the log-prob of
         # the sampled action and V(s) are by-products of the step (bit-identical to the separate pass); without RND the rewards are
         # final too, so the GAE returns are computed right here on the time-major planes (coalesced across envs)
         fuse_eval = bool(getattr(ppo, "fuse_evaluation", False)) and not d.is_continuous
-        ops.rollout(env.sim, buf, ppo.policy_old.flat, ppo._action_scale(), ppo._seed, env.episode, self._scores, evaluate=fuse_eval)
+        ops.rollout(env.sim, buf, ppo.policy_old.flat, ppo._action_scale(), ppo._seed, env.episode, self._scores, evaluate=fuse_eval,
+                    auto_reset_horizon=horizon, steps=T)
         with_returns = fuse_eval and not ppo.use_RND
         if with_returns:
             ops.gae_columns(buf.rewards, buf.dones, buf.values, buf.lengths, ppo.gamma, ppo.GAE_lambda, out=buf.returns)

@@ -33,13 +33,9 @@ __device__ __forceinline__ void store_obs_row(float *__restrict__ obs, size_t ro
 }
 
 // ------------------------------------------------------------------------------------------------ reset
+// start state of env e in episode `episode`: numpy Generator.uniform(low, high) arithmetic on Philox(seed; e, episode) doubles
 template <class ENV>
-__global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__restrict__ state,
-                            int32_t *__restrict__ elapsed, uint8_t *__restrict__ terminal, float *__restrict__ obs) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    Philox ph(seed);
-    double s[ENV::S];
+__device__ __forceinline__ void draw_reset(const Philox &ph, int e, uint64_t episode, double (&s)[ENV::S]) {
     uint32_t r[4];
 #pragma unroll
     for (int i = 0; i < ENV::S; ++i) {
@@ -52,6 +48,16 @@ __global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__re
         if (ENV::RESET_F32) v = (double)(float)v;
         s[i] = v;
     }
+}
+
+template <class ENV>
+__global__ void k_env_reset(int E, uint64_t seed, uint64_t episode, double *__restrict__ state,
+                            int32_t *__restrict__ elapsed, uint8_t *__restrict__ terminal, float *__restrict__ obs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    Philox ph(seed);
+    double s[ENV::S];
+    draw_reset<ENV>(ph, e, episode, s);
     store_state<ENV>(state, E, e, s);
     elapsed[e] = 0;
     terminal[e] = 0;
@@ -87,14 +93,6 @@ __global__ void k_env_reset_numpy(int E, const uint64_t *__restrict__ seeds, uin
     float o[ENV::O];
     ENV::obs(s, o);
     store_obs_row<ENV>(obs, e, o);
-}
-
-// test hook: out[i][k] = k-th 64-bit output of PCG64(SeedSequence(seeds[i]))
-__global__ void k_test_pcg64(const uint64_t *__restrict__ seeds, int n, int draws, uint64_t *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Pcg64 g = Pcg64::from_seed(seeds[i]);
-    for (int k = 0; k < draws; ++k) out[(size_t)i * draws + k] = g.next64();
 }
 
 template <class ENV>
@@ -442,7 +440,7 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
           uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
           uint8_t *__restrict__ terminal, float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
           float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores, float *__restrict__ blp,
-          float *__restrict__ bv) {
+          float *__restrict__ bv, int horizon) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = TAPED ? TPB : EV_THREADS;
     EvSmem S{};
@@ -462,6 +460,12 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
     if (valid) load_state<ENV>(state, E, e, s);
     double rsum = 0.0;
     int len = 0;
+    // horizon > 0: opt-in AUTO-RESET (not the reference's worker, which lets finished envs drop out - AsyncPPO.py:118,143-146): an
+    // env whose episode ends (terminated, or `horizon` = the TimeLimit steps into the episode) is reset in place and goes on, so
+    // every env fills all T_cap slots; the slot at T_cap - 1 closes the last episode (done = 1) like a truncation.  The k-th
+    // in-rollout reset of an env draws what reset() would draw in episode `episode | k << 40`.
+    int ep_t = 0;
+    uint32_t resets = 0;
     Philox ph(seed);
     for (int t = 0; t < T_cap; ++t) {
         float o[ENV::O];
@@ -518,7 +522,9 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
             }
             double r64;
             const bool term = ENV::step(s, a, r64);
-            const bool fin = term || (t + 1 >= T_cap);
+            ++ep_t;
+            const bool over = horizon > 0 && (term || ep_t >= horizon);   // auto-reset: this episode is over, the env is not
+            const bool fin = horizon > 0 ? (over || t + 1 >= T_cap) : (term || t + 1 >= T_cap);
 #pragma unroll
             for (int c = 0; c < ENV::O; ++c) bs[((size_t)t * ENV::O + c) * E + e] = o[c];
             ba[(size_t)t * E + e] = a_store;
@@ -526,7 +532,12 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
             bd[(size_t)t * E + e] = fin ? 1.f : 0.f;
             rsum += r64;
             len = t + 1;
-            alive = !fin;
+            alive = horizon > 0 ? (t + 1 < T_cap) : !fin;
+            if (over && alive) {
+                ++resets;
+                draw_reset<ENV>(ph, e, episode | ((uint64_t)resets << 40), s);
+                ep_t = 0;
+            }
         }
     }
     if (valid) {
@@ -568,12 +579,6 @@ int prl_env_reset_numpy(int env_id, int E, const uint64_t *seeds, uint64_t *rng,
         k_env_reset_numpy<ENV><<<cdiv(E, TPB), TPB, 0, (cudaStream_t)stream>>>(E, seeds, rng, state, elapsed, terminal, obs);
         return check_launch("k_env_reset_numpy");
     });
-}
-
-int prl_test_pcg64(const uint64_t *seeds, int n, int draws, uint64_t *out, void *stream) {
-    PRL_REQUIRE(seeds && out && n > 0 && draws > 0, "prl_test_pcg64: bad arguments");
-    k_test_pcg64<<<cdiv(n, TPB), TPB, 0, (cudaStream_t)stream>>>(seeds, n, draws, out);
-    return check_launch("k_test_pcg64");
 }
 
 int prl_env_set_state(int env_id, int E, const double *state_aos, double *state, int32_t *elapsed, uint8_t *terminal,
@@ -750,16 +755,17 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
                 const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
                 float *buf_rewards, float *buf_dones, int32_t *lengths, double *scores, void *stream) {
     return prl_rollout_eval(env_id, E, T_cap, params, action_scaling, seed, episode, tape, state, elapsed, terminal, buf_states, buf_actions,
-                            buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, stream);
+                            buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, 0, stream);
 }
 
 int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
                      const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
                      float *buf_rewards, float *buf_dones, float *buf_logp, float *buf_values, int32_t *lengths, double *scores,
-                     void *stream) {
+                     int auto_reset_horizon, void *stream) {
     PRL_REQUIRE(E > 0 && T_cap > 0 && state && elapsed && terminal && buf_states && buf_actions && buf_rewards && buf_dones &&
                     lengths && scores, "prl_rollout: bad arguments");
     PRL_REQUIRE(tape || params, "prl_rollout: need policy parameters or an action tape");
+    PRL_REQUIRE(auto_reset_horizon >= 0 && episode < (1ull << 40), "prl_rollout_eval: bad auto_reset_horizon / episode");
     PRL_REQUIRE((buf_logp == nullptr) == (buf_values == nullptr) && !(tape && buf_logp),
                 "prl_rollout_eval: buf_logp and buf_values go together and need the policy (no action tape)");
     return dispatch_env(env_id, [&](auto env) -> int {
@@ -769,7 +775,7 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
         if (tape) {
             k_rollout<ENV, true><<<cdiv(E, TPB), TPB, 0, st>>>(E, T_cap, params, L, action_scaling, seed, episode, tape, state, elapsed,
                                                               terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores,
-                                                              nullptr, nullptr);
+                                                              nullptr, nullptr, auto_reset_horizon);
         } else {
             PRL_REQUIRE(!(buf_logp && ENV::CONT && ENV::A != 1), "prl_rollout_eval: continuous envs with action_dim > 1 are evaluated by prl_policy_evaluate");
             const size_t smem = (size_t)ev_layout(L, buf_logp ? L.n_heads : L.n_heads - 1).total * sizeof(float);
@@ -777,7 +783,7 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
             PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
                                                                  elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
-                                                                 lengths, scores, buf_logp, buf_values);
+                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon);
         }
         return check_launch("k_rollout");
     });

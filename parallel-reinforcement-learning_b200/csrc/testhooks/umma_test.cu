@@ -1,8 +1,8 @@
 // Parity-test hook for the tensor-core building blocks (csrc/umma.cuh): one CTA stages fp32 matrices in the
 // row-per-thread shared-memory layout, issues tcgen05.mma kind::f16 (bf16) in each of the operand-major combinations the
 // fused update kernel uses, and returns the accumulator.  Test infrastructure behind prl_test_umma.
-#include "common.cuh"
-#include "umma.cuh"
+#include "../common.cuh"
+#include "../umma.cuh"
 
 namespace prl {
 using namespace umma;

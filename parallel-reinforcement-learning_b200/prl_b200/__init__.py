@@ -6,6 +6,6 @@
 The drop-in packages `PPO` and `AsyncTools` (same import paths as the reference) sit next to this package.
 """
 from ._lib import PrlError, env_info, load_library  # noqa: F401
-from .envs import make  # noqa: F401
+from .envs import make, play  # noqa: F401
 
-__all__ = ["PrlError", "env_info", "load_library", "make"]
+__all__ = ["PrlError", "env_info", "load_library", "make", "play"]

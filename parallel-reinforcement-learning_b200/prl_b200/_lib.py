@@ -9,6 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprl_b200.so")
+TEST_LIB_PATH = os.path.join(_HERE, "libprl_b200_test.so")
 
 ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3}
 ACT_I32, ACT_I64, ACT_F32 = 0, 1, 2
@@ -46,7 +47,7 @@ PROTOTYPES = {
     "prl_policy_act": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "prl_policy_evaluate": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "prl_rollout": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "prl_rollout_eval": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "prl_rollout_eval": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64] + [_vp] * 12 + [_i32, _vp]),
     "prl_gae": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp, _sz, _vp]),
     "prl_gae_ws_bytes": (_sz, [_i64]),
     "prl_gae_columns": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _vp, _vp]),
@@ -73,11 +74,30 @@ PROTOTYPES = {
     "prl_rnd_grad": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
 }
 
+TEST_FUNCTIONS = ("prl_test_sincos", "prl_test_pow2", "prl_test_philox", "prl_test_umma", "prl_test_pcg64")   # libprl_b200_test.so
+
 _lib = None
+_test_lib = None
 
 
 class PrlError(RuntimeError):
     pass
+
+
+def load_test_library(path: str | None = None):
+    """The parity-test hooks (include/prl_b200_test.h): a separate library, never loaded by the product path."""
+    global _test_lib
+    if _test_lib is None:
+        path = path or TEST_LIB_PATH
+        if not os.path.exists(path):
+            raise PrlError(f"{path} is missing - run `python __graft_entry__.py` (build()) first")
+        lib = C.CDLL(path)
+        for name in TEST_FUNCTIONS:
+            fn_ = getattr(lib, name)
+            fn_.restype, fn_.argtypes = PROTOTYPES[name]
+        lib.prl_test_last_error.restype = C.c_char_p
+        _test_lib = lib
+    return _test_lib
 
 
 def load_library(path: str | None = None):
@@ -90,6 +110,8 @@ def load_library(path: str | None = None):
         raise PrlError(f"{path} is missing - run `python __graft_entry__.py` (build()) first; there is no CPU fallback")
     lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
+        if name in TEST_FUNCTIONS:
+            continue
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype, fn.argtypes = res, args
     _lib = lib
@@ -129,7 +151,8 @@ def profile_calls(enable: bool):
 
 def call(name: str, *args):
     """Invoke a status-returning entry point; raise PrlError with prl_last_error() on failure."""
-    lib = load_library()
+    is_test = name in TEST_FUNCTIONS
+    lib = load_test_library() if is_test else load_library()
     CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
     import torch
 
@@ -142,7 +165,7 @@ def call(name: str, *args):
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:
-        raise PrlError(f"{name} failed ({rc}): {lib.prl_last_error().decode()}")
+        raise PrlError(f"{name} failed ({rc}): {(lib.prl_test_last_error() if is_test else lib.prl_last_error()).decode()}")
 
 
 def launches(counts: dict[str, int] | None = None) -> int:

@@ -37,12 +37,79 @@ class EnvDescriptor:
     def close(self):
         pass
 
+    # ---- the gymnasium single-env surface, for playback loops like the reference's Test.py:19-33 (`state, _ = env.reset()`,
+    # `env.step(action)`): ONE env on the device, stepped by the same kernels as the vectorised path (batch 1) -----------------
+    def _single(self):
+        if getattr(self, "_sim1", None) is None:
+            import torch
+
+            from . import ops
+
+            self._sim1 = ops.EnvState(self.env_id, 1, self.max_episode_steps)
+            self._seed1 = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self._episode1, self._numpy1 = 0, False
+            self._idx1 = torch.zeros(1, dtype=torch.int32, device=self._sim1.state.device)
+        return self._sim1
+
+    def reset(self, seed=None, options=None):
+        """-> (observation float32 [O], info).  seed: gymnasium's env.reset(seed=...) stream (numpy PCG64, bit for bit)."""
+        import torch
+
+        sim = self._single()
+        self._episode1 += 1
+        if seed is not None:
+            self._numpy1 = True
+            obs = sim.reset_numpy(torch.from_numpy(np.asarray([seed], dtype=np.uint64).view(np.int64)).to(sim.state.device))
+        elif self._numpy1:
+            obs = sim.reset_numpy()
+        else:
+            obs = sim.reset(self._seed1, self._episode1)
+        return obs[0].cpu().numpy(), {}
+
+    def step(self, action):
+        """-> (observation, reward, terminated, truncated, info) like gymnasium (TimeLimit included)."""
+        import torch
+
+        sim = self._single()
+        a = np.asarray(action)
+        if self.is_continuous:
+            a_dev = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(1, -1)).to(sim.state.device)
+        else:
+            a_dev = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64).reshape(1)).to(sim.state.device)
+        obs, reward, done, trunc = sim.step(self._idx1, 1, a_dev)
+        return obs[0].cpu().numpy(), float(reward[0].item()), bool(done[0].item()), bool(trunc[0].item()), {}
+
+    def render(self):
+        return None
+
     def __repr__(self):
         return f"EnvDescriptor({self.env_id!r}, max_episode_steps={self.max_episode_steps})"
 
 
 def make(env_id: str, max_episode_steps: int | None = None, **_ignored) -> EnvDescriptor:
     return EnvDescriptor(env_id, max_episode_steps)
+
+
+def play(ppo, env, episodes: int = 1, seed=None, on_step=None):
+    """The reference's Test.py loop (Test.py:19-33) as a helper: batch-1 `ppo.get_action` + `env.step` until done | truncate,
+    `episodes` times.  Returns the list of episode rewards.  on_step(state, action, reward, done) is called after every step
+    (Test.py renders and updates a progress bar there)."""
+    import torch
+
+    totals = []
+    for ep in range(int(episodes)):
+        state, _ = env.reset(seed=None if seed is None else seed + ep)
+        total = 0.0
+        while True:
+            action = ppo.get_action(torch.from_numpy(state).unsqueeze(0))
+            state, reward, done, truncate, _ = env.step(action.squeeze(0))
+            total += reward
+            if on_step is not None:
+                on_step(state, action, reward, done or truncate)
+            if done or truncate:
+                break
+        totals.append(total)
+    return totals
 
 
 def describe(env) -> EnvDescriptor:

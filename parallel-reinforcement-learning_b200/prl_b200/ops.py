@@ -240,15 +240,18 @@ def policy_evaluate(params, is_continuous, O, A, states, actions, entropy_sum=No
     return logp, value, entropy_sum
 
 
-def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, episode, scores, tape=None, evaluate=False):
+def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, episode, scores, tape=None, evaluate=False, auto_reset_horizon=0, steps=None):
     """Fused AsyncPPO.worker(): one launch.  scores: float64[2] device tensor, accumulated.  evaluate: also fill buf.logp / buf.values
-    (the old-policy evaluation of PPO.learn, bit-identical to policy_evaluate on the same rows)."""
+    (the old-policy evaluation of PPO.learn, bit-identical to policy_evaluate on the same rows).  auto_reset_horizon > 0: opt-in
+    auto-reset (every env fills all buf.T slots; an episode ends at termination or after that many steps)."""
     if evaluate:
         buf.want_eval()
-    call("prl_rollout_eval", env.code, env.E, buf.T, _ptr(params), float(action_scaling or 1.0), seed, episode, _ptr(tape),
+    T = buf.T if steps is None else int(steps)
+    assert 0 < T <= buf.T
+    call("prl_rollout_eval", env.code, env.E, T, _ptr(params), float(action_scaling or 1.0), seed, episode, _ptr(tape),
          _ptr(env.state), _ptr(env.elapsed), _ptr(env.terminal), _ptr(buf.states), _ptr(buf.actions), _ptr(buf.rewards),
          _ptr(buf.dones), _ptr(buf.logp) if evaluate else None, _ptr(buf.values) if evaluate else None, _ptr(buf.lengths),
-         _ptr(scores, torch.float64), _stream())
+         _ptr(scores, torch.float64), int(auto_reset_horizon), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ GAE

@@ -327,6 +327,75 @@ def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
         assert np.array_equal(bits(a.rnd.pred_flat.cpu().numpy()), bits(b.rnd.pred_flat.cpu().numpy()))
 
 
+def test_auto_reset_worker_opt_in(api):
+    """AsyncPPO.auto_reset (opt-in; the default stays the reference's drop-out worker): exactly num_envs x rollout_steps transitions
+    per worker(), several episodes per env column, by-products (log-prob, value, GAE returns over columns with dones in the
+    middle) still the bits of the separate passes, learn() consumes them."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    from prl_b200 import ops
+
+    t.manual_seed(5)
+    ppo = P.PPO(is_continuous=False, observ_dim=4, action_dim=2, k_epochs=2, batch_size=64, mini_batch_size=4096)
+    ppo.show_progress = False
+    ap = A.AsyncPPO.AsyncPPO(env=prl.make("CartPole-v1", max_episode_steps=50), ppo=ppo, num_envs=200, steps=1)
+    ap.worker()
+    n_ref = len(ppo.memory.states)           # reference semantics: one episode per env, ragged
+    assert 200 <= n_ref < 200 * 50
+    ppo.memory.clear()
+    ap.auto_reset, ap.rollout_steps = True, 80
+    ap.step_score = 0
+    ap.worker()
+    m = ppo.memory
+    N = m._dev_count
+    assert N == 200 * 80 == int(ap.step_score)
+    states, actions, rewards, dones = m.device_view(4, 1, ppo.device)
+    d = dones.cpu().numpy().reshape(200, 80)
+    assert d[:, -1].all() and d.sum() > 2 * 200          # every column closed; untrained CartPole: several episodes per env
+    runs = np.diff(np.concatenate([[-1], np.flatnonzero(d[0])]))   # episode lengths of env 0
+    assert runs.max() <= 50
+    pre = m.evaluated(N, ppo._eval_tag())
+    assert pre is not None
+    logp, value, _ = ops.policy_evaluate(ppo.policy_old.flat, False, 4, 2, states, actions)
+    ret = ops.gae(rewards, dones, value, ppo.gamma, ppo.GAE_lambda)
+    for got, want in zip(pre, (logp, value, ret)):
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want.cpu().numpy()))
+    before = ppo.policy.flat.clone()
+    ppo.learn()
+    assert len(m.states) == 0 and not t.equal(before, ppo.policy.flat) and bool(t.isfinite(ppo.policy.flat).all())
+
+
+@pytest.mark.parametrize("key", ["cartpole", "pendulum", "acrobot", "mountaincar"])
+def test_batch1_playback_loop_like_test_py(api, key):
+    """The reference's Test.py loop (Test.py:19-33): `state, _ = env.reset()`, batch-1 `ppo.get_action`, `env.step(action)` until
+    done | truncate - on the single-env surface of the descriptor gym.make hands out.  Seeded like gymnasium (numpy stream), the
+    trace must be the oracle env's, bit for bit, under the same actions."""
+    P, prl = api["PPO"], api["prl"]
+    from oracle import envs as oenvs
+
+    env = prl.make(ENVS[key], max_episode_steps=60)
+    cont = env.is_continuous
+    t.manual_seed(2)
+    ppo = P.PPO(is_continuous=cont, observ_dim=env.observ_dim, action_dim=env.action_dim, action_scaling=2.0 if cont else None)
+    ref = oenvs.make(ENVS[key], max_episode_steps=60)
+    state, _ = env.reset(seed=123)
+    want, _ = ref.reset(seed=123)
+    assert state.dtype == np.float32 and np.array_equal(bits(state), bits(np.asarray(want, np.float32)))
+    steps = 0
+    while True:
+        action = ppo.get_action(t.from_numpy(state).unsqueeze(0))
+        assert action.shape == ((1, env.action_dim) if cont else (1,))
+        state, reward, done, truncate, _ = env.step(action.squeeze(0))
+        w_state, w_reward, w_done, w_trunc, _ = ref.step(action.squeeze(0))
+        steps += 1
+        assert np.array_equal(bits(state), bits(np.asarray(w_state, np.float32))) and reward == float(w_reward), steps
+        assert done == bool(w_done) and truncate == bool(w_trunc), steps
+        if done or truncate:
+            break
+    assert 1 <= steps <= 60
+    totals = prl.play(ppo, env, episodes=2, seed=5)
+    assert len(totals) == 2 and all(np.isfinite(totals))
+
+
 def test_reference_unittest_call_patterns(api):
     """The duck-typing the reference's own unittests rely on."""
     A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]

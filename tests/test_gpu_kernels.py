@@ -193,6 +193,50 @@ def test_fused_rollout_matches_c_oracle(ops, key, E, T):
     assert np.array_equal(bits(got["actions"].reshape(want["actions"].shape)), bits(want["actions"]))
 
 
+@pytest.mark.parametrize("key,horizon", [("cartpole", 40), ("pendulum", 25), ("acrobot", 30), ("mountaincar", 35)])
+def test_auto_reset_rollout_matches_oracle_episodes(ops, key, horizon):
+    """Opt-in auto-reset (north_star; NOT the reference's worker): every env fills all T slots, an env whose episode ends is reset
+    in place.  Checked against the oracle run episode by episode: env e's k-th episode starts from what prl_env_reset draws in
+    episode `episode | k << 40`, consumes the tape where the previous one stopped, ends at termination / `horizon` steps / the
+    last slot (done = 1)."""
+    env_id = ENVS[key]
+    E, T, seed, episode = 96, 96, 77, 3
+    rng = np.random.default_rng(5)
+    d = cref.env_dims(env_id)
+    cont = bool(d["continuous"])
+    tape = (2 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32) if cont else rng.integers(0, d["A"], (T, E)).astype(np.int32)
+    sim = ops.EnvState(env_id, E, horizon)
+    starts = []
+    for k in range(T):   # start state of every env's k-th episode (k = 0: the ordinary reset of this episode)
+        sim.reset(seed, episode | (k << 40))
+        starts.append(sim.get_state().cpu().numpy())
+        if k == 0:
+            first = starts[0]
+    sim.set_state(dev(first))
+    aw = d["A"] if cont else 1
+    buf = ops.RolloutBuffer(E, T, d["O"], aw)
+    scores = t.zeros(2, dtype=t.float64, device="cuda")
+    ops.rollout(sim, buf, None, 1.0, seed, episode, scores, tape=dev(tape), auto_reset_horizon=horizon)
+    assert (buf.lengths.cpu().numpy() == T).all() and int(scores[1].item()) == E * T
+    gs, ga, gr, gd = (x.cpu().numpy() for x in (buf.states, buf.actions, buf.rewards, buf.dones))
+    n_resets = 0
+    for e in range(E):
+        off, k = 0, 0
+        while off < T:
+            ms = min(horizon, T - off)
+            tp = np.ascontiguousarray(tape[off:off + ms, e:e + 1])
+            w = cref.rollout(env_id, starts[k][e:e + 1], tp, ms)
+            L = w["N"]
+            assert np.array_equal(bits(gs[off:off + L, :, e]), bits(w["states"])), (e, k)
+            assert np.array_equal(bits(gr[off:off + L, e]), bits(w["rewards"])) and np.array_equal(bits(gd[off:off + L, e]), bits(w["dones"]))
+            assert np.array_equal(bits(ga[off:off + L, :, e].reshape(w["actions"].shape)), bits(w["actions"]))
+            off += L
+            k += 1
+        n_resets += k - 1
+    assert n_resets >= E      # the case is not vacuous: on average every env was reset at least once
+    assert gd[T - 1].all()    # the last slot closes every env's running episode
+
+
 # ------------------------------------------------------------------------------------------------ utils kernels
 def test_compaction_and_mask_update(ops):
     rng = np.random.default_rng(1)

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "parallel-reinforcement-learning_b200")
 
 
-def header_symbols():
-    src = open(os.path.join(ROOT, "include", "prl_b200.h")).read()
+def header_symbols(name="prl_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(prl_[a-z0-9_]+)\s*\(", src)))
 
@@ -29,7 +29,15 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/prl_b200.h but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
-    assert sorted(_lib.PROTOTYPES) == names  # and nothing is bound that the header does not declare
+        assert not n.startswith("prl_test_"), "test hooks do not belong in the product library"
+    # the parity-test hooks live in their own library with their own header; the product exports none of them
+    tlib = _lib.load_test_library()
+    tnames = header_symbols("prl_b200_test.h")
+    assert sorted(tnames) == sorted(_lib.TEST_FUNCTIONS + ("prl_test_last_error",))
+    for n in tnames:
+        assert hasattr(tlib, n), f"{n} declared in include/prl_b200_test.h but not exported"
+        assert not hasattr(lib, n), f"{n} leaked into the product library"
+    assert sorted(_lib.PROTOTYPES) == sorted(names + list(_lib.TEST_FUNCTIONS))  # nothing is bound that no header declares
     assert lib.prl_version() == 100
 
 
