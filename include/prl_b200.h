@@ -162,8 +162,11 @@ int prl_ppo_grad(const float *params, int is_continuous, int obs_dim, int action
                  float policy_clip, float inv_count, float *grad, double *loss_out, float *ws, size_t ws_floats,
                  void *stream);
 /* Tensor-core form of prl_ppo_grad (csrc/update_tc.cu): same contract and gradient layout; tcgen05.mma (bf16x3 split
- * operands, fp32 accumulation in tensor memory) for every contraction over features or rows.  Discrete policies with
- * observ_dim <= 16 and action_dim <= 8 (prl_ppo_grad_tc_supported).  The workspace must be zeroed once before its first
+ * operands, fp32 accumulation in tensor memory) for every contraction over features or rows.  Policies with
+ * observ_dim <= 16 and action_dim <= 8; prl_ppo_grad_tc_supported returns 1 for discrete policies (every form below), 2 for
+ * continuous ones (prl_ppo_grad_tc only: a float32 forward pre-pass evaluates the tanh-Gaussian loss and its gradient with
+ * respect to the mu / log_std head outputs, then the two-head kernel runs twice - {mu, critic} and {log_std, critic weighted 0} -
+ * and the two reduced gradients are added; ActorCritic.py:28-42), 0 otherwise.  The workspace must be zeroed once before its first
  * use: ws[0] is a sticky status word that prl_ppo_grad_tc_status (host-synchronising) reads - 1 if a tensor-core phase
  * of any call never completed. */
 int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim);

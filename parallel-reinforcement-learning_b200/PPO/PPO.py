@@ -84,8 +84,9 @@ class PPO:
         self._grad = t.zeros_like(self.policy.flat)
         self._ws = None
         self._rows = None
-        # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies), "fp32" = CUDA-core
-        # FMA kernel (csrc/update_ppo.cu; every configuration).  Same math and tolerances, two members of one family.
+        # minibatch-gradient kernel: "tensor" = tcgen05 kernel (csrc/update_tc.cu; discrete policies in one fused launch per step,
+        # continuous ones as a pre-pass + two passes of the same kernel), "fp32" = CUDA-core FMA kernel (csrc/update_ppo.cu; every
+        # configuration).  Same math and tolerances, two members of one family.
         self.peer_exchange = True     # sharded tensor path: gradient exchange over peer memory inside the step kernel
         self._xch = None
         self.fused_optimizer = True   # tensor path, single process: one launch per optimiser step (prl_ppo_step_tc)
@@ -249,8 +250,9 @@ class PPO:
             counts = [min(N - k * mb, mb) for k in range(n_mb)]
 
         use_tc = self.update_path == "tensor"
-        if use_tc and not ops.tc_supported(cont, O, A):
-            raise ValueError("update_path='tensor' supports discrete policies with observ_dim <= 16 and action_dim <= 8")
+        tc_level = ops.tc_supported(cont, O, A)
+        if use_tc and not tc_level:
+            raise ValueError("update_path='tensor' supports policies with observ_dim <= 16 and action_dim <= 8")
         grad_fn = ops.ppo_grad_tc if use_tc else ops.ppo_grad
         need = (ops.update_tc_ws_floats if use_tc else ops.update_ws_floats)(cont, O, A, min(mb_local, N))
         if self._ws is None or self._ws.numel() < need:
@@ -260,10 +262,10 @@ class PPO:
         self._ws_owner = self.update_path
         steps = self.k_epochs * n_mb
 
-        fused = use_tc and comm is None and self.fused_optimizer   # gradient + clip + AdamW in one cooperative launch
+        fused = use_tc and tc_level == 1 and comm is None and self.fused_optimizer   # gradient + clip + AdamW in one cooperative launch
         # sharded: the same single launch, with the gradient exchange over NVLink peer memory inside it (no NCCL per step) -
         # when every rank sits on this host and all GPU pairs have peer access; otherwise the NCCL allreduce path below
-        p2p = use_tc and comm is not None and self.fused_optimizer and self.peer_exchange
+        p2p = use_tc and tc_level == 1 and comm is not None and self.fused_optimizer and self.peer_exchange
         if p2p:
             if self._p2p_ok is None:
                 self._p2p_ok = pdist.peer_access_possible(comm)

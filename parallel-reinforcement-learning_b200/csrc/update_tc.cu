@@ -39,6 +39,7 @@
 #include <string.h>
 
 #include "policy.cuh"
+#include "tiled_mlp.cuh"
 #include "umma.cuh"
 
 namespace prl {
@@ -286,6 +287,17 @@ __device__ __forceinline__ void tmem_st16_f2(uint32_t taddr, const f2 (&v)[8]) {
 // The LEADER CTA (the last one: it owns no slice when the grid is larger than the slice count) collects those, and
 // publishes the clip coefficient as one tagged word that everybody else polls; then every CTA applies clip_grad_norm_ +
 // AdamW to its slices.  One launch per optimiser step instead of three; no grid barrier, no host-side reset.
+// Continuous policies (mu head, log_std head, critic: ActorCritic.py:28-42) run through this two-head kernel as TWO passes over
+// the minibatch.  Their loss couples the mu and log_std outputs, so a forward pre-pass (k_policy_dout) evaluates the loss and
+// leaves d loss / d mu and d loss / d log_std per row; given those, the heads are independent: pass 1 = {mu head with its
+// external output gradient, critic with its own SmoothL1}, pass 2 = {log_std head with its external gradient, critic weighted 0}.
+// Everything downstream of the output gradient is linear in it, so the trunk's gradient is the sum of the two passes'.
+struct TcExternal {
+    const float *dout;      // [b][out of head 0] gradient of the loss w.r.t. head 0's outputs (inv_count included); nullptr: discrete loss
+    float critic_weight;    // 1: the critic's SmoothL1 term takes part; 0: its output gradient is zero (second pass)
+    int zero_off, zero_len; // range of the partial-gradient row that belongs to the head this pass does not touch: written as zeros
+};
+
 struct TcOptimizer {
     float *params_rw, *grad, *m, *v;          // params_rw == nullptr: gradient only (the reduction runs as a separate kernel)
     int64_t *clock;                           // {int64 step, double beta1^step, double beta2^step}
@@ -442,7 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
               float clip, float inv_count, float *__restrict__ partials, int part_stride, double *__restrict__ loss_partials,
-              int *__restrict__ status, TcOptimizer opt, int qpc) {
+              int *__restrict__ status, TcOptimizer opt, int qpc, TcExternal ext) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[6];          // MMA completion: actor forward, actor backward, critic dgrad, trunk wgrad, critic wgrad, critic forward
     __shared__ uint64_t sbar[4];          // operands staged (512 arrivals): F + X, actor DZ, critic DZ, trunk DZ
@@ -652,9 +664,10 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 #pragma unroll
                 for (int i = 0; i < XR; ++i) xn[i] = (nlive && i < O) ? __ldg(states + rown * O + i) : 0.f;
             }
-            const float adv_i = live ? __ldg(adv + row) : 0.f, old_i = live ? __ldg(old_logp + row) : 0.f;
+            const bool own_loss = ext.dout == nullptr;   // (warp-uniform) false: head 0's output gradient comes from the pre-pass
+            const float adv_i = (live && own_loss) ? __ldg(adv + row) : 0.f, old_i = (live && own_loss) ? __ldg(old_logp + row) : 0.f;
             const float ret_i = live ? __ldg(returns + row) : 0.f;
-            const int act = live ? (int)__ldg(actions + row) : 0;
+            const int act = (live && own_loss) ? (int)__ldg(actions + row) : 0;
 
             // ================= trunk forward (CUDA cores): z0 = W0c x, GroupNorm, SiLU -> F pieces, X pieces; zhat0 and SiLU'
             // are parked in tensor memory for the trunk backward
@@ -778,7 +791,13 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 float dout[NO];
 #pragma unroll
                 for (int a = 0; a < NO; ++a) dout[a] = 0.f;
-                if (H == 0) {
+                if (H == 0 && !own_loss) {
+                    if (live) {
+#pragma unroll
+                        for (int a = 0; a < NO; ++a)
+                            if (a < nout) dout[a] = __ldg(ext.dout + row * nout + a);
+                    }
+                } else if (H == 0) {
                     if (live) {
                         float m = out[0];
 #pragma unroll
@@ -818,8 +837,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     }
                 } else if (live) {
                     const float dv = out[0] - ret_i, ad = fabsf(dv);
-                    if (q == 0) l_val += ad < 1.f ? 0.5f * dv * dv : ad - 0.5f;
-                    dout[0] = 0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f));
+                    if (q == 0) l_val += ext.critic_weight * (ad < 1.f ? 0.5f * dv * dv : ad - 0.5f);
+                    dout[0] = ext.critic_weight * (0.5f * inv_count * (ad < 1.f ? dv : (dv > 0.f ? 1.f : -1.f)));
                 }
                 // ---- dy = (dout . W2) * SiLU'(y), in place of ds
 #pragma unroll
@@ -986,6 +1005,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             }
             part[off + j] = sm;
         }
+        for (int idx = tid; idx < ext.zero_len; idx += TC_COMPUTE) part[ext.zero_off + idx] = 0.f;
         if (tid < NA) {
             if (tid < nout0) part[L.head[0].b2 + tid] = (b2s[0][tid] + b2s[1][tid]) + (b2s[2][tid] + b2s[3][tid]);
         } else if (tid == NA) {
@@ -1155,7 +1175,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 // tail above: used when the gradient is needed on its own, e.g. for the allreduce of the sharded path.)
 __global__ void __launch_bounds__(64 * RED_SL)
 k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int stride, float *__restrict__ grad,
-                     const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows) {
+                     const double *__restrict__ loss_partials, double *__restrict__ loss_out, double rows, int accumulate) {
     __shared__ float part[RED_SL][64];
     const int p = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + p;
@@ -1165,9 +1185,84 @@ k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int
         float t[RED_SL];
 #pragma unroll
         for (int u = 0; u < RED_SL; ++u) t[u] = part[u][p];
-        grad[i] = reduce_tree(t);
+        const float g = reduce_tree(t);
+        grad[i] = accumulate ? grad[i] + g : g;
     }
     if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) add_loss_sums(loss_partials, nblocks, loss_out, rows, threadIdx.x);
+}
+
+// ---- pre-pass of the continuous (tanh-Gaussian) update: forward of trunk + mu head + log_std head in IEEE float32 (the
+// register-tiled forward of the old-policy evaluation, tiled_mlp.cuh), the clipped-surrogate loss of every row and its gradient
+// with respect to the two heads' outputs - the operation sequence of csrc/update_ppo.cu's continuous branch (PPO.py:219-252,
+// ActorCritic.py:118-146).  dout_mu / dout_ls [b][A]; loss_partials[block][4] = {policy term sum, 0, entropy sum, 0}.
+__global__ void __launch_bounds__(EV_THREADS, 2)
+k_policy_dout(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
+              const float *__restrict__ old_logp, const float *__restrict__ adv, int64_t n, float clip, float inv_count,
+              float *__restrict__ dout_mu, float *__restrict__ dout_ls, double *__restrict__ loss_partials) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double red[32];
+    const EvSmem S = ev_layout(L, 2);   // mu and log_std heads (the critic's loss needs no pre-pass)
+    const int tid = threadIdx.x, O = L.O, A = L.A;
+    ev_stage_weights(smem, S, params, L);
+    float *sX = smem + S.x;
+    const float *sO = smem + S.out;
+    const int64_t ntiles = (n + EV_ROWS - 1) / EV_ROWS;
+    double pol_acc = 0.0, ent_acc = 0.0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t row0 = tile * EV_ROWS;
+        const int rows = (int)min((int64_t)EV_ROWS, n - row0);
+        __syncthreads();
+        for (int i = tid; i < EV_ROWS * O; i += EV_THREADS) sX[i] = i < rows * O ? __ldg(states + row0 * O + i) : 0.f;
+        __syncthreads();
+        ev_forward_tile(smem, S, L);
+        __syncthreads();
+        if (tid < rows) {
+            const int64_t row = row0 + tid;
+            const float *o = sO + tid * S.so;
+            // From the float32 head outputs on, the loss and its output gradients are evaluated in DOUBLE: ratio = exp(logp - old_logp)
+            // carries ulp(|logp|) of float32 noise per row otherwise, which the Gaussian log-density's (z^2 - 1) / sigma factors
+            // amplify (measured on the learn_continuous rows: 5e-5 of the largest gradient component in float32, torch-float32
+            // autograd itself 1e-5; a few dozen double operations per row cost nothing next to the forward)
+            double q = 0.0, hld = 0.0;
+            for (int a = 0; a < A; ++a) {
+                const double mu = (double)o[S.col[0] + a], ls = (double)o[S.col[1] + a];
+                const double lc = fmin(fmax(ls, -2.0), 2.0);
+                const double tril = log1p(exp(lc));            // softplus; sqrt(sd^2) = sd > 0
+                const double zt = ((double)actions[row * A + a] - mu) / tril;
+                q = fma(zt, zt, q);
+                hld += log(tril);
+            }
+            const double logp = -0.5 * (A * 1.8378770664093454836 + q) - hld;
+            // d(-min(r A, clamp(r) A) * inv_count) / dlogp
+            const double adv_i = (double)adv[row], dl = logp - (double)old_logp[row], lo = 1.0 - (double)clip, hi = 1.0 + (double)clip;
+            const double r = exp(fmin(fmax(dl, -20.0), 20.0));
+            const double s1 = r * adv_i, s2 = fmin(fmax(r, lo), hi) * adv_i;
+            const double g1 = s1 < s2 ? 1.0 : (s1 > s2 ? 0.0 : 0.5);   // torch.min splits ties evenly
+            const double in_clip = (r >= lo && r <= hi) ? 1.0 : 0.0;
+            const double in20 = (dl >= -20.0 && dl <= 20.0) ? 1.0 : 0.0;
+            const double dlogp = -(double)inv_count * adv_i * (g1 + (1.0 - g1) * in_clip) * r * in20;
+            for (int a = 0; a < A; ++a) {
+                const double mu = (double)o[S.col[0] + a], ls = (double)o[S.col[1] + a];
+                const double lc = fmin(fmax(ls, -2.0), 2.0);
+                const double tril = log1p(exp(lc));
+                const double zt = ((double)actions[row * A + a] - mu) / tril;
+                const double in2 = (ls >= -2.0 && ls <= 2.0) ? 1.0 : 0.0;
+                dout_mu[row * A + a] = (float)(dlogp * zt / tril);
+                dout_ls[row * A + a] = (float)(dlogp * (zt * zt - 1.0) / tril * (1.0 / (1.0 + exp(-lc))) * in2);
+            }
+            pol_acc += -fmin(s1, s2);
+            ent_acc += 0.5 * A * (1.0 + 1.8378770664093454836) + hld;
+        }
+    }
+    const double bp = block_sum<double>(pol_acc, red);
+    const double be = block_sum<double>(ent_acc, red);
+    if (tid == 0) {
+        loss_partials[blockIdx.x * 4 + 0] = bp; loss_partials[blockIdx.x * 4 + 1] = 0.0;
+        loss_partials[blockIdx.x * 4 + 2] = be; loss_partials[blockIdx.x * 4 + 3] = 0.0;
+    }
+}
+__global__ void k_add_loss_sums(const double *__restrict__ loss_partials, int nblocks, double *__restrict__ loss_out) {
+    add_loss_sums(loss_partials, nblocks, loss_out, 0.0, threadIdx.x);
 }
 
 // Row split.  The minibatch is cut into 32-row quarters (one per row-quarter warp group); CTA c owns the TC_QPC consecutive
@@ -1216,25 +1311,34 @@ using namespace prl;
 
 extern "C" {
 
+// 1: discrete policy - every form (prl_ppo_grad_tc, prl_ppo_step_tc, prl_ppo_step_tc_p2p); 2: continuous policy - prl_ppo_grad_tc
+// only (pre-pass + two passes of the two-head kernel); 0: not supported
 int prl_ppo_grad_tc_supported(int is_continuous, int obs_dim, int action_dim) {
-    return !is_continuous && obs_dim >= 1 && obs_dim <= TC_MAX_O && action_dim >= 1 && action_dim <= TC_MAX_A;
+    const bool fits = obs_dim >= 1 && obs_dim <= TC_MAX_O && action_dim >= 1 && action_dim <= TC_MAX_A;
+    return fits ? (is_continuous ? 2 : 1) : 0;
 }
+
+// continuous: behind the kernel's workspace sit d loss / d mu and d loss / d log_std of every row ([b][A] each) and the pre-pass's
+// loss partials (4 doubles per CTA, at most 2 CTAs per SM)
+static size_t tc_cont_extra_floats(int action_dim, int64_t batch) { return (size_t)2 * action_dim * batch + 8 * 2 * 160 + 16; }
 
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    return tc_ws_floats(L, tc_grid_max(batch));
+    return tc_ws_floats(L, tc_grid_max(batch)) + (is_continuous ? tc_cont_extra_floats(action_dim, batch) : 0);
 }
 
 // shared launcher: gradient only (opt == nullptr: + separate reduction kernel) or fused optimiser step
-static int launch_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
+// L: the two heads the kernel works on (a discrete policy's own layout, or two of a continuous policy's three heads inside the
+// full parameter vector); ext: where head 0's output gradient comes from; accumulate: add the reduced gradient to `grad`
+static int launch_tc(const float *params, const PolicyLayout &L, const float *states, const float *actions,
                      const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
-                     float *grad, double *loss_out, float *ws, size_t ws_floats, cudaStream_t st, const TcOptimizer *optp, const char *who) {
+                     float *grad, double *loss_out, float *ws, size_t ws_floats, cudaStream_t st, const TcOptimizer *optp, const char *who,
+                     TcExternal ext = TcExternal{nullptr, 1.0f, 0, 0}, int accumulate = 0) {
     PRL_REQUIRE(params && grad && ws && b >= 0 && (b > 0 || (optp && optp->world > 1)), "%s: bad arguments", who);
-    PRL_REQUIRE(b == 0 || (states && actions && old_logp && adv && returns), "%s: null row pointer", who);
-    PRL_REQUIRE(prl_ppo_grad_tc_supported(is_continuous, obs_dim, action_dim),
-                "%s: only discrete policies with observ_dim <= %d and action_dim <= %d (got continuous=%d O=%d A=%d)", who, TC_MAX_O,
-                TC_MAX_A, is_continuous, obs_dim, action_dim);
-    const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
+    PRL_REQUIRE(b == 0 || (states && returns && (ext.dout || (actions && old_logp && adv))), "%s: null row pointer", who);
+    const int obs_dim = L.O, action_dim = L.A;
+    PRL_REQUIRE(prl_ppo_grad_tc_supported(0, obs_dim, action_dim) && L.n_heads == 2,
+                "%s: policies with observ_dim <= %d and action_dim <= %d only (got O=%d A=%d)", who, TC_MAX_O, TC_MAX_A, obs_dim, action_dim);
     int grid, qpc;
     tc_split(b, &grid, &qpc);
     const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
@@ -1266,7 +1370,7 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
         attr[0].val.cooperative = optp ? 1 : 0;
         cfg.attrs = attr; cfg.numAttrs = 1;
         PRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, partials, pstride,
-                                    loss_partials, status, opt, qpc));
+                                    loss_partials, status, opt, qpc, ext));
         return PRL_OK;
     };
     const bool x4 = obs_dim <= 4;
@@ -1298,15 +1402,54 @@ static int launch_tc(const float *params, int is_continuous, int obs_dim, int ac
         if (optp) fprintf(stderr, "[%s] tail: arrival counted %llu..%llu | all arrivals seen %llu..%llu | slices reduced %llu..%llu | norm known %llu..%llu\n", who,
                           mn[4], mx[4], mn[5], mx[5], mn[6], mx[6], mn[7], mx[7]);
     }
-    if (!optp) k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out, (double)b);
+    if (!optp) k_reduce_partials_tc<<<cdiv(L.total, 64), 64 * RED_SL, 0, st>>>(partials, grid, L.total, pstride, grad, loss_partials, loss_out,
+                                                                               ext.critic_weight != 0.f ? (double)b : 0.0, accumulate);
     return check_launch(who);
 }
 
 int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
                     const float *old_logp, const float *adv, const float *returns, int64_t b, float policy_clip, float inv_count,
                     float *grad, double *loss_out, float *ws, size_t ws_floats, void *stream) {
-    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
-                     ws, ws_floats, (cudaStream_t)stream, nullptr, "prl_ppo_grad_tc");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!is_continuous)
+        return launch_tc(params, make_policy_layout(0, obs_dim, action_dim), states, actions, old_logp, adv, returns, b, policy_clip, inv_count,
+                         grad, loss_out, ws, ws_floats, st, nullptr, "prl_ppo_grad_tc");
+    // ---- continuous policy: pre-pass (loss + output gradients of the mu / log_std heads), then two passes of the two-head kernel
+    const char *who = "prl_ppo_grad_tc (continuous)";
+    PRL_REQUIRE(prl_ppo_grad_tc_supported(1, obs_dim, action_dim), "%s: observ_dim <= %d and action_dim <= %d only", who, TC_MAX_O, TC_MAX_A);
+    PRL_REQUIRE(params && states && actions && old_logp && adv && returns && grad && ws && b > 0, "%s: bad arguments", who);
+    const PolicyLayout LC = make_policy_layout(1, obs_dim, action_dim);
+    const size_t base = tc_ws_floats(LC, tc_grid_max(b));
+    PRL_REQUIRE(ws_floats >= base + tc_cont_extra_floats(action_dim, b) && ((uintptr_t)ws & 15) == 0, "%s: workspace too small / unaligned", who);
+    const size_t off_mu = (base + 3) & ~(size_t)3, off_ls = off_mu + (size_t)action_dim * b, off_pre = (off_ls + (size_t)action_dim * b + 3) & ~(size_t)3;
+    float *dmu = ws + off_mu, *dls = ws + off_ls;
+    double *pre_partials = reinterpret_cast<double *>(ws + off_pre);   // (ws is 16-byte aligned, off_pre a multiple of 4 floats)
+    {
+        const size_t smem = (size_t)ev_layout(LC, 2).total * sizeof(float);
+        PRL_REQUIRE(smem <= 227 * 1024, "%s: pre-pass needs %zu B shared memory", who, smem);
+        PRL_CUDA(cudaFuncSetAttribute(k_policy_dout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t ntiles = cdiv(b, EV_ROWS);
+        const int pgrid = (int)(ntiles < 2 * sms ? ntiles : (2 * sms < 320 ? 2 * sms : 320));
+        k_policy_dout<<<pgrid, EV_THREADS, smem, st>>>(params, LC, states, actions, old_logp, adv, b, policy_clip, inv_count, dmu, dls, pre_partials);
+        if (loss_out) k_add_loss_sums<<<1, 32, 0, st>>>(pre_partials, pgrid, loss_out);
+        if (check_launch("k_policy_dout") != PRL_OK) return PRL_ERR_CUDA;
+    }
+    // the kernel's view of the parameter vector: trunk + {one policy head, critic}
+    auto two_heads = [&](int h) {
+        PolicyLayout L2 = LC;
+        L2.cont = 0; L2.n_heads = 2;
+        L2.head[0] = LC.head[h]; L2.head[1] = LC.head[2];
+        return L2;
+    };
+    const int span = HID * HID + 2 * HID + action_dim * HID + action_dim;   // parameters of one policy head (contiguous: w1 gw gb w2 b2)
+    int rc = launch_tc(params, two_heads(0), states, nullptr, nullptr, nullptr, returns, b, policy_clip, inv_count, grad, loss_out, ws, base, st, nullptr, who,
+                       TcExternal{dmu, 1.0f, LC.head[1].w1, span}, 0);
+    if (rc != PRL_OK) return rc;
+    return launch_tc(params, two_heads(1), states, nullptr, nullptr, nullptr, returns, b, policy_clip, inv_count, grad, nullptr, ws, base, st, nullptr, who,
+                     TcExternal{dls, 0.0f, LC.head[0].w1, span}, 1);
 }
 
 int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_dim, const float *states, const float *actions,
@@ -1317,7 +1460,8 @@ int prl_ppo_step_tc(float *params, int is_continuous, int obs_dim, int action_di
     TcOptimizer opt{};
     opt.params_rw = params; opt.grad = grad; opt.m = exp_avg; opt.v = exp_avg_sq; opt.clock = step_counter; opt.norm_out = grad_norm_out;
     opt.lr = lr; opt.wd = weight_decay; opt.max_norm = max_norm; opt.loss_out = loss_out; opt.rows = (double)b;
-    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
+    PRL_REQUIRE(!is_continuous, "prl_ppo_step_tc: discrete policies only (continuous ones: prl_ppo_grad_tc + prl_adamw_step_dev)");
+    return launch_tc(params, make_policy_layout(0, obs_dim, action_dim), states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
                      ws, ws_floats, (cudaStream_t)stream, &opt, "prl_ppo_step_tc");
 }
 
@@ -1333,7 +1477,8 @@ int prl_ppo_step_tc_p2p(float *params, int is_continuous, int obs_dim, int actio
     opt.params_rw = params; opt.grad = grad; opt.m = exp_avg; opt.v = exp_avg_sq; opt.clock = step_counter; opt.norm_out = grad_norm_out;
     opt.lr = lr; opt.wd = weight_decay; opt.max_norm = max_norm; opt.loss_out = loss_out; opt.rows = (double)b;
     opt.peers = reinterpret_cast<float *const *>(peer_bufs); opt.rank = rank; opt.world = world; opt.gstride = (L.total + 3) & ~3;
-    return launch_tc(params, is_continuous, obs_dim, action_dim, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
+    PRL_REQUIRE(!is_continuous, "prl_ppo_step_tc_p2p: discrete policies only (continuous ones: prl_ppo_grad_tc + allreduce + prl_adamw_step_dev)");
+    return launch_tc(params, L, states, actions, old_logp, adv, returns, b, policy_clip, inv_count, grad, loss_out,
                      ws, ws_floats, (cudaStream_t)stream, &opt, "prl_ppo_step_tc_p2p");
 }
 

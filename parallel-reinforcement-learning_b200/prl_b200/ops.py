@@ -299,7 +299,9 @@ def ppo_grad(params, is_continuous, O, A, states, actions, old_logp, adv, return
 
 
 def tc_supported(is_continuous, O, A):
-    return bool(_lib.fn("prl_ppo_grad_tc_supported")(int(is_continuous), int(O), int(A)))
+    """0: no tensor-core update for this policy; 1: every form (gradient, fused step, sharded fused step); 2: the gradient form only
+    (continuous policies: pre-pass + two passes of the two-head kernel inside prl_ppo_grad_tc)."""
+    return int(_lib.fn("prl_ppo_grad_tc_supported")(int(is_continuous), int(O), int(A)))
 
 
 def update_tc_ws_floats(is_continuous, O, A, batch):

@@ -61,12 +61,16 @@ def make_ppo(api, g, **kw):
     return p
 
 
-@pytest.mark.parametrize("name,roll", [("discrete", "cartpole"), ("continuous", "pendulum"), ("rnd", "acrobot"),
-                                       ("discrete_1step", "cartpole"), ("continuous_1step", "pendulum")])
-def test_learn_matches_reference_post_update_weights(api, golden, name, roll, capsys):
-    """PPO.learn() on the reference's memory contents -> the reference's post-update weights and AdamW moments."""
+@pytest.mark.parametrize("name,roll,path", [("discrete", "cartpole", "tensor"), ("continuous", "pendulum", "tensor"), ("rnd", "acrobot", "tensor"),
+                                            ("discrete_1step", "cartpole", "tensor"), ("continuous_1step", "pendulum", "tensor"),
+                                            ("continuous", "pendulum", "fp32"), ("continuous_1step", "pendulum", "fp32"), ("discrete", "cartpole", "fp32")])
+def test_learn_matches_reference_post_update_weights(api, golden, name, roll, path, capsys):
+    """PPO.learn() on the reference's memory contents -> the reference's post-update weights and AdamW moments, through the
+    tensor-core update (the default for every BASELINE policy) and through the fp32-FMA one."""
     g, r = golden("learn_" + name), golden("rollout_" + roll)
     ppo = make_ppo(api, g)
+    assert ppo.update_path == "tensor"
+    ppo.update_path = path
     for i in range(len(r["states"])):  # fill PPO.memory the way buffer_to_target_buffer_transfer does (float32 items)
         ppo.memory.states.append(r["states"][i].copy())
         ppo.memory.actions.append(r["actions"][i].copy())
