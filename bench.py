@@ -443,7 +443,7 @@ def run_b200(args):
         flops_row = 3.0 * 2 * (pp["observ_dim"] * 64 + 2 * 64 * 64 + 64 * heads_out + 64)   # = 51 840 at CartPole shapes
         tf = rows_epochs * flops_row / (g["ms"] * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_tc_traffic.json")   # dram__bytes_read + write of one launch (ncu --set full capture)
+        tpath = os.path.join(ROOT, "profiles", "r02_tc_traffic.json")   # dram__bytes_read + write of one launch (ncu --set full capture)
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]

@@ -290,7 +290,7 @@ class AsyncPPO:
         # the old-policy evaluation of PPO.learn (PPO.py:134-154) rides along: the acting policy IS policy_old, so the log-prob of
         # the sampled action and V(s) are by-products of the step (bit-identical to the separate pass); without RND the rewards are
         # final too, so the GAE returns are computed right here on the time-major planes (coalesced across envs)
-        fuse_eval = bool(getattr(ppo, "fuse_evaluation", False)) and not d.is_continuous
+        fuse_eval = bool(getattr(ppo, "fuse_evaluation", False)) and (not d.is_continuous or d.action_dim == 1)
         ops.rollout(env.sim, buf, ppo.policy_old.flat, ppo._action_scale(), ppo._seed, env.episode, self._scores, evaluate=fuse_eval,
                     auto_reset_horizon=horizon, steps=T)
         with_returns = fuse_eval and not ppo.use_RND

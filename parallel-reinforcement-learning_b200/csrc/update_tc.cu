@@ -108,8 +108,9 @@ __device__ __forceinline__ void store_pieces16(unsigned char *base, int r, int q
     }
 }
 
-// column sum of 8 per-row values over the warp's 32 rows: on return every lane holds the total of feature
-// f(lane) = 4*bit4 + 2*bit3 + bit2 of its lane index (4 lanes hold each feature).  9 shuffles.
+// column sum of 8 per-row values over the warp's 32 rows, first three butterfly levels: on return lane l holds the sum over the 8
+// lanes that share l's bits 0 and 1 of feature f(lane) = 4*bit4 + 2*bit3 + bit2.  The sum over the remaining four lanes (xor 2,
+// xor 1) is linear, so it is taken ONCE per launch on the accumulated values (colsum_finish) instead of once per tile.  7 shuffles.
 __device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
     const int lane = threadIdx.x & 31;
     const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
@@ -119,14 +120,17 @@ __device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3,
     const float a3 = (u16 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, u16 ? v3 : v7, 16);
     const float b0 = (u8 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, u8 ? a0 : a2, 8);
     const float b1 = (u8 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, u8 ? a1 : a3, 8);
-    float c0 = (u4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, u4 ? b0 : b1, 4);
-    c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
-    c0 += __shfl_xor_sync(0xffffffffu, c0, 1);
-    return c0;
+    return (u4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, u4 ? b0 : b1, 4);
+}
+// the deferred levels of colsum8, applied to a register accumulator at the end of the launch: afterwards all four lanes holding a
+// feature hold its total
+__device__ __forceinline__ void colsum_finish(f2 &acc) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
 }
 // column sums of the thread's 16 features (8 pairs) over the warp's 32 rows, added to the lane's register accumulators:
-// acc.x += total of feature f(lane) of group 0, acc.y += the same of group 1 (all four lanes holding a feature keep it: no
-// divergent update, nothing in memory; the accumulators live across all tiles of the CTA)
+// acc.x += partial total of feature f(lane) of group 0, acc.y += the same of group 1 (no divergent update, nothing in memory; the
+// accumulators live across all tiles of the CTA and are completed by colsum_finish)
 __device__ __forceinline__ void colsum16(const f2 (&v)[8], f2 &acc) {
     acc.x += colsum8(v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y);
     acc.y += colsum8(v[4].x, v[4].y, v[5].x, v[5].y, v[6].x, v[6].y, v[7].x, v[7].y);
@@ -623,6 +627,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
 #pragma unroll
         for (int a = 0; a < NA; ++a) { acc_w2a[a] = dup2(0.f); b2a[a] = 0.f; }
         float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+        const bool softmax_rows_sum_to_zero = ext.dout == nullptr;   // head 0 is a softmax head evaluated here (not an external gradient)
 
         // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
         float xn[XR];
@@ -875,7 +880,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                     tmem_ld16_f2(lane_base + TM_HJ + j0, hj);
 #pragma unroll
                     for (int a = 0; a < NO; ++a) {
-                        if (a < nout) {
+                        if (a < nout - ((H == 0 && softmax_rows_sum_to_zero) ? 1 : 0)) {   // (softmax head: the last action follows from the others)
                             f2 t[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) t[k] = mul2(hj[k], dup2(dout[a]));
@@ -957,8 +962,24 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 for (int i = 0; i < TC_W; ++i) scratch2[r * 17 + i] = v2[i];
             }
         }
-        // column sums: one of the four lanes holding feature f of a group reports it; quantities: 0 dgamma0, 1 dbeta0, then per
-        // head: dgamma, dbeta, dW2[a] (a < out)
+        // column sums: complete the butterflies (all lanes), then one of the four lanes holding feature f of a group reports it;
+        // quantities: 0 dgamma0, 1 dbeta0, then per head: dgamma, dbeta, dW2[a] (a < out)
+        colsum_finish(acc_g0); colsum_finish(acc_b0); colsum_finish(acc_gh[0]); colsum_finish(acc_bh[0]);
+        colsum_finish(acc_gh[1]); colsum_finish(acc_bh[1]); colsum_finish(acc_w2c);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) colsum_finish(acc_w2a[a]);
+        if (softmax_rows_sum_to_zero) {
+            // the softmax head's output gradients of a row sum to zero (dout_a = dlogp (1[a = act] - p_a), sum_a p_a = 1), so the
+            // last action's dW2 row and db2 are minus the sum of the others': its column sums were skipped in the tile loop
+            f2 w = dup2(0.f);
+            float bsum = 0.f;
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                if (a < nout0 - 1) { w = add2(w, acc_w2a[a]); bsum += b2a[a]; }
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+                if (a == nout0 - 1) { acc_w2a[a] = mk2(-w.x, -w.y); b2a[a] = -bsum; }
+        }
         if ((lane & 3) == 0) {
             const int f = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             float *dst = s_red + (size_t)rq * NQ * HID + j0 + f;

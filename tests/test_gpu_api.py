@@ -278,7 +278,7 @@ def test_fused_worker_equals_stepwise_worker(api, key, cont):
     assert (f[3].sum() == 2 * E)  # every episode ends with done = 1 (termination or truncation)
 
 
-@pytest.mark.parametrize("key,rnd", [("cartpole", False), ("acrobot", False), ("acrobot", True), ("mountaincar", False)])
+@pytest.mark.parametrize("key,rnd", [("cartpole", False), ("acrobot", False), ("acrobot", True), ("mountaincar", False), ("pendulum", False)])
 def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
     """The fused worker records, per transition, the acting policy's log-prob and state value (prl_rollout_eval) and - without
     RND - the GAE returns (prl_gae_columns on the time-major planes).  They must be the bits PPO.learn's own passes produce on
@@ -290,8 +290,8 @@ def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
     def run(fuse):
         t.manual_seed(11)
         env = prl.make(ENVS[key], max_episode_steps=48)
-        ppo = P.PPO(is_continuous=False, observ_dim=env.observ_dim, action_dim=env.action_dim, k_epochs=2, batch_size=64, mini_batch_size=512,
-                    use_RND=rnd, beta=0.01)
+        ppo = P.PPO(is_continuous=env.is_continuous, observ_dim=env.observ_dim, action_dim=env.action_dim, k_epochs=2, batch_size=64,
+                    mini_batch_size=512, use_RND=rnd, beta=0.01, action_scaling=2.0 if env.is_continuous else None)
         ppo.show_progress = False
         ppo.fuse_evaluation = fuse
         ap = A.AsyncPPO.AsyncPPO(env=env, ppo=ppo, num_envs=300, steps=1)
@@ -305,7 +305,7 @@ def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
     pre = m.evaluated(N, ppo._eval_tag())
     assert pre is not None and N >= 600
     states, actions, rewards, dones = m.device_view(ppo.observ_dim, 1, ppo.device)
-    logp, value, _ = ops.policy_evaluate(ppo.policy_old.flat, False, ppo.observ_dim, ppo.action_dim, states, actions)
+    logp, value, _ = ops.policy_evaluate(ppo.policy_old.flat, ppo.is_continuous, ppo.observ_dim, ppo.action_dim, states, actions)
     assert np.array_equal(bits(pre[0].cpu().numpy()), bits(logp.cpu().numpy()))
     assert np.array_equal(bits(pre[1].cpu().numpy()), bits(value.cpu().numpy()))
     if rnd:
