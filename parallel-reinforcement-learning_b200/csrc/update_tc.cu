@@ -84,6 +84,7 @@ __device__ __forceinline__ f2 sigmoid2(f2 y) {
     const f2 d = add2(mk2(ex2_approx(t.x), ex2_approx(t.y)), dup2(1.0f));
     return mk2(rcp_approx(d.x), rcp_approx(d.y));
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float fast_exp(float x) { return ex2_approx(x * 1.4426950408889634f); }
 __device__ __forceinline__ float fast_log(float x) { return lg2_approx(x) * 0.6931471805599453f; }
 
@@ -475,6 +476,15 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     TC_STAMP(0);
     TC_SPAN(0);
     if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);   // overlaps the parameter staging of the other warps
+    else if (q == 0 && lane == 0) {
+        // the first tile's per-row scalars start their way from HBM to L2 while the parameters are staged
+        const int64_t row0 = (int64_t)blockIdx.x * qpc * 32 + r;
+        if (row0 < b) {
+            if (ext.dout == nullptr) { prefetch_l2(adv + row0); prefetch_l2(old_logp + row0); prefetch_l2(actions + row0); }
+            else prefetch_l2(ext.dout + row0 * nout0);
+            prefetch_l2(returns + row0);
+        }
+    }
 
     // ---- everything the launch needs from global memory besides the rows is requested up front (one exposed latency)
     const bool fused = opt.params_rw != nullptr;
@@ -628,6 +638,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         for (int a = 0; a < NA; ++a) { acc_w2a[a] = dup2(0.f); b2a[a] = 0.f; }
         float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
         const bool softmax_rows_sum_to_zero = ext.dout == nullptr;   // head 0 is a softmax head evaluated here (not an external gradient)
+        const bool own_loss_pf = ext.dout == nullptr;
 
         // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
         float xn[XR];
@@ -668,6 +679,14 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 const bool nlive = 4 * (tile + 1) + rq < myq && rown < b;
 #pragma unroll
                 for (int i = 0; i < XR; ++i) xn[i] = (nlive && i < O) ? __ldg(states + rown * O + i) : 0.f;
+                // the next tile's per-row scalars (one 128-byte line per array and row quarter) are pulled into L2 now: their loads
+                // at the top of the next tile would otherwise wait for HBM inside the actor epilogue (ncu: long-scoreboard samples
+                // on the first use of `actions`)
+                if (q == 0 && lane == 0 && nlive) {
+                    if (own_loss_pf) { prefetch_l2(adv + rown); prefetch_l2(old_logp + rown); prefetch_l2(actions + rown); }
+                    else prefetch_l2(ext.dout + rown * nout0);
+                    prefetch_l2(returns + rown);
+                }
             }
             const bool own_loss = ext.dout == nullptr;   // (warp-uniform) false: head 0's output gradient comes from the pre-pass
             const float adv_i = (live && own_loss) ? __ldg(adv + row) : 0.f, old_i = (live && own_loss) ? __ldg(old_logp + row) : 0.f;
