@@ -88,38 +88,55 @@ k_rnd_grad(const float *__restrict__ tparams, const float *__restrict__ pparams,
             gn_silu(ht, T.gw, T.gb);
             for (int o = 0; o < L.Oo; ++o) tgt[o] = T.b2[o] + dot64(ht, T.w2 + o * HID);
         }
-        float zhat[HID], rstd[GROUPS];
+        // predictor forward, everything the backward needs kept in registers (one pass over the hidden features: the SiLU and its
+        // derivative are evaluated ONCE per element - this kernel used to re-evaluate expf + division three more times per element
+        // for the three staging passes below): zhat, then dy[j] = SiLU'(y_j) until the output gradient is known
+        float zhat[HID], dy[HID], rstd[GROUPS];
         rnd_hidden_pre(Pn, L.I, [&](int i) { return Xcol[i * UP_NTP]; }, zhat);
         gn_normalize(zhat, rstd);
-        for (int o = 0; o < L.Oo; ++o) {
-            float acc = 0.f;
+        float acc[MAX_OUT];
 #pragma unroll
-            for (int j = 0; j < HID; ++j) acc = fmaf(silu(fmaf(zhat[j], Pn.gw[j], Pn.gb[j])), Pn.w2[o * HID + j], acc);
-            const float d = live ? (Pn.b2[o] + acc) - tgt[o] : 0.f;
-            sq += (double)d * d;
-            dout[o] = 2.0f * d * inv_count;
-        }
-        auto dy_of = [&](int j) -> float {
-            float dh = 0.f;
-            for (int o = 0; o < L.Oo; ++o) dh = fmaf(dout[o], Pn.w2[o * HID + j], dh);
+        for (int o = 0; o < MAX_OUT; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
             const float y = fmaf(zhat[j], Pn.gw[j], Pn.gb[j]);
+            const float h = silu(y);
             const float sg = 1.0f / (1.0f + expf(-y));
-            return dh * sg * fmaf(y, 1.0f - sg, 1.0f);
-        };
+            dy[j] = sg * fmaf(y, 1.0f - sg, 1.0f);
+            Zcol[j * UP_NTP] = h;
 #pragma unroll
-        for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = silu(fmaf(zhat[j], Pn.gw[j], Pn.gb[j]));
-        for (int o = 0; o < L.Oo; ++o) Dcol[o * UP_NTP] = dout[o];
+            for (int o = 0; o < MAX_OUT; ++o)
+                if (o < L.Oo) acc[o] = fmaf(h, Pn.w2[o * HID + j], acc[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < MAX_OUT; ++o) {
+            dout[o] = 0.f;
+            if (o < L.Oo) {
+                const float d = live ? (Pn.b2[o] + acc[o]) - tgt[o] : 0.f;
+                sq += (double)d * d;
+                dout[o] = 2.0f * d * inv_count;
+                Dcol[o * UP_NTP] = dout[o];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+            float dh = 0.f;
+#pragma unroll
+            for (int o = 0; o < MAX_OUT; ++o)
+                if (o < L.Oo) dh = fmaf(dout[o], Pn.w2[o * HID + j], dh);
+            dy[j] *= dh;
+        }
         __syncthreads();
         coop_outer_small(D, L.Oo, Z, HID, part + L.w2);
         coop_rowsum(D, L.Oo, part + L.b2);
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy_of(j) * zhat[j];
+        for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy[j] * zhat[j];
         __syncthreads();
         coop_rowsum(Z, HID, part + L.gw);
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy_of(j);
+        for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy[j];
         __syncthreads();
         coop_rowsum(Z, HID, part + L.gb);
         __syncthreads();
@@ -129,7 +146,7 @@ k_rnd_grad(const float *__restrict__ tparams, const float *__restrict__ pparams,
 #pragma unroll
             for (int i = 0; i < GSIZE; ++i) {
                 const int j = g * GSIZE + i;
-                d[i] = dy_of(j) * Pn.gw[j];
+                d[i] = dy[j] * Pn.gw[j];
                 m1 += d[i];
                 m2 = fmaf(d[i], zhat[j], m2);
             }
