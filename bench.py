@@ -405,7 +405,11 @@ def run_b200(args):
     step(True)  # touch the e2e path once
     clocks = ClockSampler(dev.index) if rank == 0 else None
     time.sleep(0.3)
+    ppo.update_events = []   # PPO.learn brackets its optimisation loop with CUDA events (2 per learn(): nothing next to 1 408 launches)
     n_dev, ms_dev, counts, _, (w0, w1) = timed(False, args.steps, profile=False)
+    upd = ppo.update_events
+    ppo.update_events = None
+    upd_ms, upd_launches = sum(a.elapsed_time(b) for a, b, _ in upd), sum(n for _, _, n in upd)
     clk = clocks.summary(w0, w1) if clocks else None
     n_e2e, ms_e2e, _, _, _ = timed(True, args.steps, profile=False)
     # sharded: the replicas must still be identical after the timed region (weights and AdamW moments, bit for bit)
@@ -441,7 +445,12 @@ def run_b200(args):
         pp = cfg["ppo"]
         heads_out = 2 * pp["action_dim"] if pp["is_continuous"] else pp["action_dim"]
         flops_row = 3.0 * 2 * (pp["observ_dim"] * 64 + 2 * 64 * 64 + 64 * heads_out + 64)   # = 51 840 at CartPole shapes
-        tf = rows_epochs * flops_row / (g["ms"] * 1e-3) / 1e12
+        # the dominant kernel's launch duration INSIDE the timed region: CUDA events on the launching stream around the optimisation
+        # loops of the timed learn() calls (graph replays: back-to-back launches) divided by the optimiser steps in them.  The
+        # launch-by-launch profiling step below brackets every call with its own event pair, which adds ~5 us per launch.
+        timed_launch_ms = upd_ms / max(upd_launches, 1)
+        timed_rows_epochs = n_dev / world * args.k_epochs
+        tf = timed_rows_epochs * flops_row / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else rows_epochs * flops_row / (g["ms"] * 1e-3) / 1e12
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r02_tc_traffic.json")   # dram__bytes_read + write of one launch (ncu --set full capture)
         if os.path.exists(tpath):
@@ -452,15 +461,18 @@ def run_b200(args):
                 "traffic_unit": "bytes per launch (65 536 rows: 2.1 MB of row inputs + 36 KB of parameters are the algorithmic bytes)",
                 "traffic_source": traffic_src,
                 "peak_source": pk["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
-                "algorithmic_flops_per_sample_epoch": flops_row, "avg_launch_ms": g["ms"] / g["calls"],
+                "algorithmic_flops_per_sample_epoch": flops_row, "avg_launch_ms": timed_launch_ms if upd_ms > 0 else g["ms"] / g["calls"],
+                "launches_timed": upd_launches, "avg_launch_ms_profiling_step": g["ms"] / g["calls"],
                 # what the tensor pipe really executes: every fp32-grade product is six bf16 MMAs (bf16x3 split) and the weight
                 # gradients run on stacked piece windows - 44.0 MFLOP of bf16 MMAs per 128-row tile
                 "executed_bf16_flops_per_sample_epoch": EXECUTED_BF16_FLOPS_PER_ROW,
                 "executed_bf16_tflops": tf * EXECUTED_BF16_FLOPS_PER_ROW / flops_row if gk != "prl_ppo_grad" else None,
-                "limiter": "CUDA-core epilogues (GroupNorm / SiLU / loss forward + backward, bf16x3 splitting, column sums): ncu issue slots 32 % "
-                           "busy with 4.25 warps per scheduler, tensor pipe 9 % active, DRAM 0.3 % (profiles/r01_ncu_summary_v2.txt)",
-                "share_of_step": g["ms"] / ms_prof,
-                "measured_on": "one launch-by-launch step after the timed region (the timed region replays CUDA graphs)"}
+                "limiter": "serial hand-over between CUDA-core epilogues (GroupNorm / SiLU / loss forward + backward, bf16x3 splitting, column sums) and "
+                           "the tensor core with one 17-warp CTA per SM: ncu issue slots 33 % busy (73 % inside the compute phases), tensor pipe 16 % "
+                           "active, DRAM = algorithmic bytes (profiles/r02_k_ppo_grad_tc_ncu_summary.txt, DESIGN.md section 5)",
+                "share_of_step": upd_ms / ms_dev if upd_ms > 0 else g["ms"] / ms_prof,
+                "measured_on": "CUDA events on the launching stream around the optimisation loops of the timed steps (CUDA-graph replays); "
+                               "avg_launch_ms_profiling_step: one launch-by-launch step after the timed region, one event pair per call"}
     hbm = {}
     # algorithmic bytes per transition (the fused worker adds two planes to the rollout and three fields to the transfer)
     bytes_per = {"prl_rollout": 102.0, "prl_rollout_eval": 110.0, "prl_gae": 16.0, "prl_gae_columns": 16.0, "prl_adv_normalize": 10.0,

@@ -299,6 +299,10 @@ class PPO:
             return hi - lo
 
         # (sharded runs capture the NCCL allreduce inside the graph as well when graph_collectives is set)
+        ev = None
+        if getattr(self, "update_events", None) is not None:   # (bench.py: CUDA events around the optimisation loop, on the launching stream)
+            ev = (t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True))
+            ev[0].record()
         use_graph = self.use_cuda_graph and (comm is None or self.graph_collectives or p2p) and not self.report_loss and steps >= 16 and n_mb >= 2
         pbar = tqdm(total=N * self.k_epochs, leave=False) if self.show_progress else None
         if use_graph:
@@ -365,6 +369,9 @@ class PPO:
                     step += 1
         if pbar is not None:
             pbar.close()
+        if ev is not None:
+            ev[1].record()
+            self.update_events.append((ev[0], ev[1], steps))
         status = ops.ppo_grad_tc_status(self._ws) if use_tc else 0
         self.memory.verify_transfers()   # (the status read above synchronised the stream: the transfer totals are final)
         if comm is not None and use_tc:

@@ -12,6 +12,10 @@
 // variant (__pow_fma/__powf_fma, selected by ifunc on any CPU with FMA+AVX2), every other operation rounds on its
 // own.  The operation sequence was established by reading that variant's machine code; tables: tools/gen_powtab.py.
 //
+// Attribution: the algorithm and its constants are those of the GNU C Library's pow / powf, which were contributed from the Arm
+// Optimized Routines (Copyright (C) Arm Limited; MIT OR Apache-2.0 WITH LLVM-exception upstream, LGPL-2.1-or-later in glibc).  No
+// upstream source text is included here: this file is an independent restatement of that algorithm.
+//
 // Outside the algorithm's normal-result range (x zero / subnormal / inf / nan, x*x overflowing or subnormal) the
 // result is the plain product x*x; classic-control states never get there.
 //

@@ -9,6 +9,10 @@
 // The operation sequence was established by reading that variant's machine code; the constants are the
 // algorithm's published ones; the table is produced by tools/gen_sincostab.py.
 //
+// Attribution: the algorithm and its constants are those of the GNU C Library's sin / cos, which derive from the IBM Accurate
+// Mathematical Library (Copyright (C) 2001 Free Software Foundation, Inc., written by International Business Machines Corp.;
+// LGPL-2.1-or-later).  No glibc source text is included here: this file is an independent restatement of that algorithm.
+//
 // |x| >= 105414350 (glibc's __branred path) is not implemented: classic-control angles never get there
 // (Pendulum |theta| <= pi + 8*0.05*T).  Such inputs return NaN so that a mismatch is loud, not silent.
 //
