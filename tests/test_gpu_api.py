@@ -278,8 +278,9 @@ def test_fused_worker_equals_stepwise_worker(api, key, cont):
     assert (f[3].sum() == 2 * E)  # every episode ends with done = 1 (termination or truncation)
 
 
-@pytest.mark.parametrize("key,rnd", [("cartpole", False), ("acrobot", False), ("acrobot", True), ("mountaincar", False), ("pendulum", False)])
-def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
+@pytest.mark.parametrize("key,rnd,envs", [("cartpole", False, 300), ("acrobot", False, 300), ("acrobot", True, 300), ("mountaincar", False, 300),
+                                          ("pendulum", False, 300), ("cartpole", False, 37)])   # 37 envs: the unaligned transfer / GAE paths
+def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd, envs):
     """The fused worker records, per transition, the acting policy's log-prob and state value (prl_rollout_eval) and - without
     RND - the GAE returns (prl_gae_columns on the time-major planes).  They must be the bits PPO.learn's own passes produce on
     the transferred rows (PPO.py:134-154 old-policy evaluation, :107-120 compute_gae), and learn() must end with the same
@@ -294,7 +295,7 @@ def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
                     mini_batch_size=512, use_RND=rnd, beta=0.01, action_scaling=2.0 if env.is_continuous else None)
         ppo.show_progress = False
         ppo.fuse_evaluation = fuse
-        ap = A.AsyncPPO.AsyncPPO(env=env, ppo=ppo, num_envs=300, steps=1)
+        ap = A.AsyncPPO.AsyncPPO(env=env, ppo=ppo, num_envs=envs, steps=1)
         ap.worker()
         ap.worker()   # rows of a second call land behind the first one's
         return ppo, ap
@@ -303,7 +304,7 @@ def test_fused_worker_by_products_equal_the_separate_passes(api, key, rnd):
     m = ppo.memory
     N = m._dev_count
     pre = m.evaluated(N, ppo._eval_tag())
-    assert pre is not None and N >= 600
+    assert pre is not None and N >= 2 * envs
     states, actions, rewards, dones = m.device_view(ppo.observ_dim, 1, ppo.device)
     logp, value, _ = ops.policy_evaluate(ppo.policy_old.flat, ppo.is_continuous, ppo.observ_dim, ppo.action_dim, states, actions)
     assert np.array_equal(bits(pre[0].cpu().numpy()), bits(logp.cpu().numpy()))
