@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprl_b200.so")
+LIB_PATH = os.environ.get("PRL_B200_LIB") or os.path.join(_HERE, "libprl_b200.so")   # (PRL_B200_LIB: A/B experiments with another build)
 TEST_LIB_PATH = os.path.join(_HERE, "libprl_b200_test.so")
 
 ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3}
