@@ -112,6 +112,7 @@ __device__ __forceinline__ void store_pieces16(unsigned char *base, int r, int q
 // column sum of 8 per-row values over the warp's 32 rows, first three butterfly levels: on return lane l holds the sum over the 8
 // lanes that share l's bits 0 and 1 of feature f(lane) = 4*bit4 + 2*bit3 + bit2.  The sum over the remaining four lanes (xor 2,
 // xor 1) is linear, so it is taken ONCE per launch on the accumulated values (colsum_finish) instead of once per tile.  7 shuffles.
+// (A/B, round 2: the same function NOT inlined - 9 KB less code - costs 4.9 %: call overhead beats instruction-cache relief)
 __device__ __forceinline__ float colsum8(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
     const int lane = threadIdx.x & 31;
     const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
@@ -518,6 +519,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                   n_h1 = 2 * HID + L.head[1].out * HID + L.head[1].out, n_small = n_small1 + n_h0 + n_h1;
         if (!is_mma_warp) {
             // thread (r, q) stages features 16q..16q+15 of row n = r of the stacked [128][64] W1 (n < 64: actor, else critic)
+            // (A/B, round 2: rotating the row every CTA starts with, so that the 147 CTAs do not ask L2 for the same lines at once, changes
+            // nothing - 0.1 %: the set-up is not bound by an L2 hot spot)
             const int w1off = (r >> 6) ? L.head[1].w1 : L.head[0].w1;   // (no dynamic index into the kernel-parameter struct)
             const float *wrow = params + w1off + (r & 63) * HID + j0;
             TC_STAMP(19);
@@ -1154,8 +1157,13 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             sq[tid] = (double)gi * gi;
         }
         __syncthreads();
-        if (tid == 0)
-            for (int k = 0; k < nc; ++k) ssum += sq[k];
+        // the 64 squared gradients of the slice: one warp, fixed tree (A/B: 0.4 % over one thread adding them serially)
+        if (warp == 0) {
+            double a = (lane < nc ? sq[lane] : 0.0) + (lane + 32 < nc ? sq[lane + 32] : 0.0);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) ssum += a;
+        }
         __syncthreads();
     }
     // a CTA that failed publishes nothing: the others time out on its squared norm, nobody applies the step
