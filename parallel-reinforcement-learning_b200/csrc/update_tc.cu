@@ -321,6 +321,12 @@ struct TcOptimizer {
     int rank, world, gstride;
 };
 
+__device__ __noinline__ double ipow(double base, int64_t n) {
+    double r = 1.0;
+    for (; n > 0; n >>= 1, base *= base)
+        if (n & 1) r *= base;
+    return r;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long v;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
@@ -455,7 +461,9 @@ __device__ unsigned long long g_tc_span[160 * 8];
 // ===================================================================================================== the kernel
 // NA = compile-time bound of the actor's output width (action_dim rounded up to 2, 4 or 8): the per-output loops unroll over
 // it.  XR = observation values kept in registers (4 or 8; observ_dim > XR reads the rest on demand).
-template <int NA, int XR>
+// SHARDED: the build with the cross-GPU gradient exchange in its tail (prl_ppo_step_tc_p2p); the single-GPU build leaves that code out
+// (the instruction stream is larger than the instruction cache as it is).
+template <int NA, int XR, bool SHARDED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
@@ -646,6 +654,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         const bool own_loss_pf = ext.dout == nullptr;
 
         // inputs of the first tile; inside the loop the next tile's are prefetched while the current one computes
+        // (A/B, round 2: requesting them before the parameter staging instead gains nothing, L2-resident or streaming)
         float xn[XR];
         {
             const int64_t row0 = row_base + r;
@@ -1085,8 +1094,10 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     {   // this step's bias-correction powers (kept off the critical path above)
         const bool have = opt_step > 0 && opt_p1 > 0.0;
         opt_step += 1;
-        opt_p1 = have ? opt_p1 * 0.9 : pow(0.9, (double)opt_step);
-        opt_p2 = have ? opt_p2 * 0.999 : pow(0.999, (double)opt_step);
+        // (first step, or a clock loaded without its powers: beta^step by binary exponentiation - an inlined double-precision pow() is
+        // ~6 KB of code in a kernel whose instruction stream is already larger than it should be; A/B: 0.6 %)
+        opt_p1 = have ? opt_p1 * 0.9 : ipow(0.9, opt_step);
+        opt_p2 = have ? opt_p2 * 0.999 : ipow(0.999, opt_step);
     }
     // The parameters are cut into slices of RC = 64 (142 slices for P = 9 027); CTA c owns slices c, c + nb, ...  The cut does
     // not depend on the grid, so ranks whose minibatches have different row counts (different grids) agree on it.
@@ -1095,7 +1106,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     float *sl_part = reinterpret_cast<float *>(smem_raw);             // [RED_SL][RC] slice sums
     double *sq = reinterpret_cast<double *>(smem_raw + 8192);         // [RC] squared gradients
     double ssum = 0.0;                                                // thread 0: squared norm of this CTA's slices
-    const bool sharded = opt.world > 1;
+    const bool sharded = SHARDED && opt.world > 1;
     // losses of the whole launch (one warp of CTA 0)
     if (blockIdx.x == 0 && is_mma_warp && opt.loss_out && tags_ok) add_loss_sums(loss_partials, nb, opt.loss_out, opt.rows, lane);
     // sharded: exchange buffer of rank r = inbox[2 (step parity)][world (sender)][gstride] 8-byte words {float bits, step number}
@@ -1424,9 +1435,15 @@ static int launch_tc(const float *params, const PolicyLayout &L, const float *st
         return PRL_OK;
     };
     const bool x4 = obs_dim <= 4;
-    const int rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4>) : launch(k_ppo_grad_tc<2, 8>))
-                 : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4>) : launch(k_ppo_grad_tc<4, 8>))
-                           : launch(k_ppo_grad_tc<8, 8>);
+    int rc;
+    if (optp && optp->world > 1)
+        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, true>) : launch(k_ppo_grad_tc<2, 8, true>))
+           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, true>) : launch(k_ppo_grad_tc<4, 8, true>))
+                     : launch(k_ppo_grad_tc<8, 8, true>);
+    else
+        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false>) : launch(k_ppo_grad_tc<2, 8, false>))
+           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false>) : launch(k_ppo_grad_tc<4, 8, false>))
+                     : launch(k_ppo_grad_tc<8, 8, false>);
     if (rc != PRL_OK) return rc;
     if (getenv("PRL_TC_TIMING")) {
         long long c[32];

@@ -22,7 +22,27 @@ if path == "step":   # fused gradient + clip + AdamW (cooperative launch), eager
     opt = FusedAdamW(params, 1e-4)
     ws = t.zeros(ops.update_tc_ws_floats(False, O, A, N), device="cuda")
     fn = lambda: ops.ppo_step_tc(params, False, O, A, s, a, logp, adv, ret, 0.2, 1.0 / N, grad, loss, opt, ws)
-    if os.environ.get("PRL_PROF_GRAPH"):
+    if os.environ.get("PRL_PROF_STREAM"):
+        # every launch of the replayed graph works on its OWN minibatch: 96 x N rows (200 MB at N = 65 536, more than the L2), as
+        # inside PPO.learn - the launches of the plain graph mode below re-read one L2-resident minibatch
+        K = 96
+        S = t.from_numpy(rng.uniform(-1, 1, (K * N, O)).astype(np.float32)).cuda()
+        Aa = t.from_numpy(rng.integers(0, A, (K * N, 1)).astype(np.float32)).cuda()
+        LP, _, _ = ops.policy_evaluate(params, False, O, A, S, Aa)
+        AD = t.randn(K * N, device="cuda"); RT = t.randn(K * N, device="cuda")
+        side = t.cuda.Stream(); side.wait_stream(t.cuda.current_stream())
+        gr = t.cuda.CUDAGraph()
+        fn()
+        with t.cuda.stream(side):
+            gr.capture_begin()
+            for k in range(K):
+                sl = slice(k * N, (k + 1) * N)
+                ops.ppo_step_tc(params, False, O, A, S[sl], Aa[sl], LP[sl], AD[sl], RT[sl], 0.2, 1.0 / N, grad, loss, opt, ws)
+            gr.capture_end()
+        t.cuda.current_stream().wait_stream(side)
+        fn = gr.replay
+        N = N * K
+    elif os.environ.get("PRL_PROF_GRAPH"):
         side = t.cuda.Stream(); side.wait_stream(t.cuda.current_stream())
         gr = t.cuda.CUDAGraph()
         with t.cuda.stream(side):
