@@ -20,7 +20,7 @@ int prl_test_pcg64(const uint64_t *seeds, int n, int draws, uint64_t *out, void 
 int prl_test_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out4, void *stream);
 /* tensor-core building blocks (csrc/umma.cuh): one 128-row tile, tcgen05.mma kind::tf32 from shared memory.
  * mode 0: D[128][128] = A[128][64] B[128][64]^T; 1: D[128][64] = A[128][64] B[64:128][0:64]; 2: D[128][64] =
- * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[16]
+ * A[128][128]^T B[128][64]; 3: D[128][16] = A[128][128]^T B[128][16]; -1: raw descriptor parameters in cfg_host[17]
  * (see csrc/umma_test.cu).  *status != 0: the MMA never completed. */
 int prl_test_umma(int mode, const float *A, const float *B, float *D, int *status, const int32_t *cfg_host, void *stream);
 

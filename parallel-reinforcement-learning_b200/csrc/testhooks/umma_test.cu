@@ -37,7 +37,8 @@ struct UmmaTestCfg {
     int a_cols, b_cols, n_out;
     uint32_t idesc;
     int nsteps, a_off, a_step, a_lbo, a_sbo, b_off, b_step, b_lbo, b_sbo;
-    int a_layout, b_layout, reps;
+    int a_layout, b_layout, reps;   // reps < 0: |reps| repetitions of the weight-stationary form (tcgen05.mma.ws)
+    int d_lane;                     // lane offset of the accumulator address (0 for the product's layouts)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -73,12 +74,18 @@ k_test_umma(UmmaTestCfg c, const float *__restrict__ A, const float *__restrict_
         }
         const uint32_t idesc = c.idesc;
         const int nsteps = c.nsteps;
+        const bool ws = c.reps < 0;
+        const int reps = ws ? -c.reps : c.reps;
+        const uint32_t dst = tmem + ((uint32_t)c.d_lane << 16);
         t0 = clock64();
         if (elect_one()) {
-            for (int rep = 0; rep < c.reps; ++rep) {
+            for (int rep = 0; rep < reps; ++rep) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s)
-                    if (s < nsteps) mma_bf16_ss(tmem, da[s], db[s], idesc, (rep | s) != 0);
+                    if (s < nsteps) {
+                        if (ws) mma_bf16_ss_ws(dst, da[s], db[s], idesc, (rep | s) != 0);
+                        else mma_bf16_ss(dst, da[s], db[s], idesc, (rep | s) != 0);
+                    }
             }
             mma_commit(&bar);
         }
@@ -112,19 +119,20 @@ extern "C" int prl_test_umma(int mode, const float *A, const float *B, float *D,
     constexpr int CH = umma::CHUNK;
     switch (mode) {
         // forward, two heads stacked along N: A, B K-major, 4 K-steps of 16 features
-        case 0: c = {64, 64, 128, idesc_bf16(128, 128, 0, 0), 4, 0, 2 * CH, CH, 128, 0, 2 * CH, CH, 128, 0, 0, 1}; break;
+        case 0: c = {64, 64, 128, idesc_bf16(128, 128, 0, 0), 4, 0, 2 * CH, CH, 128, 0, 2 * CH, CH, 128, 0, 0, 1, 0}; break;
         // dgrad of head 1: A K-major; B'[n' = k][K' = j] = W[64 + j][k] is the MN-major view of the same weight buffer
-        case 1: c = {64, 64, 64, idesc_bf16(128, 64, 0, 1), 4, 0, 2 * CH, CH, 128, 64 * 16, 256, 128, CH, 0, 0, 1}; break;
+        case 1: c = {64, 64, 64, idesc_bf16(128, 64, 0, 1), 4, 0, 2 * CH, CH, 128, 64 * 16, 256, 128, CH, 0, 0, 1, 0}; break;
         // weight gradient: contraction over the 128 rows, both operands MN-major, 8 K-steps of 16 rows
-        case 2: c = {128, 64, 64, idesc_bf16(128, 64, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1}; break;
-        case 3: c = {128, 16, 16, idesc_bf16(128, 16, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1}; break;
+        case 2: c = {128, 64, 64, idesc_bf16(128, 64, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1, 0}; break;
+        case 3: c = {128, 16, 16, idesc_bf16(128, 16, 1, 1), 8, 0, 256, 128, CH, 0, 256, 128, CH, 0, 0, 1, 0}; break;
         default:
-            PRL_REQUIRE(cfg_host, "prl_test_umma: mode -1 needs cfg_host[16]");
+            PRL_REQUIRE(cfg_host, "prl_test_umma: mode -1 needs cfg_host[17]");
             c = {cfg_host[0], cfg_host[1], cfg_host[2], (uint32_t)cfg_host[3], cfg_host[4], cfg_host[5], cfg_host[6], cfg_host[7],
-                 cfg_host[8], cfg_host[9], cfg_host[10], cfg_host[11], cfg_host[12], cfg_host[13], cfg_host[14], cfg_host[15]};
+                 cfg_host[8], cfg_host[9], cfg_host[10], cfg_host[11], cfg_host[12], cfg_host[13], cfg_host[14], cfg_host[15], cfg_host[16]};
     }
     PRL_REQUIRE(c.a_cols % 8 == 0 && c.a_cols <= 128 && c.b_cols % 8 == 0 && c.b_cols <= 64 && c.n_out % 16 == 0 && c.n_out <= 128 &&
-                    c.nsteps >= 1 && c.nsteps <= 8 && c.reps >= 1 && c.reps <= 4096 && (c.a_layout | c.b_layout | 2) == 2,
+                    c.nsteps >= 1 && c.nsteps <= 8 && c.reps != 0 && c.reps >= -4096 && c.reps <= 4096 && (c.a_layout | c.b_layout | 2) == 2 &&
+                    c.d_lane >= 0 && c.d_lane < 128,
                 "prl_test_umma: configuration out of range");
     const size_t smem = 48 * 1024 + 1024;
     PRL_CUDA(cudaFuncSetAttribute(k_test_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

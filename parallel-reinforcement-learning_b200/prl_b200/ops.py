@@ -77,7 +77,8 @@ def test_umma(mode, A, B, cfg=None):
     status = torch.zeros(2, dtype=torch.int32, device=_dev())   # [0] = timed out, [1] = cycles from first issue to completion
     if cfg is not None:
         cfg = list(cfg) + [0, 0, 1][len(cfg) - 13:] if len(cfg) < 16 else list(cfg)
-    cfg_arr = (C.c_int32 * 16)(*[int(x) for x in cfg]) if cfg is not None else None
+        cfg = cfg + [0] * (17 - len(cfg))   # [16]: lane offset of the accumulator address
+    cfg_arr = (C.c_int32 * 17)(*[int(x) for x in cfg]) if cfg is not None else None
     call("prl_test_umma", -1 if cfg is not None else mode, _ptr(A, torch.float32), _ptr(B, torch.float32), _ptr(D), _ptr(status),
          cfg_arr, _stream())
     st = status.cpu().numpy()
