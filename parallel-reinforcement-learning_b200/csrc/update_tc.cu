@@ -300,7 +300,7 @@ __device__ __forceinline__ void tmem_st16_f2(uint32_t taddr, const f2 (&v)[8]) {
 // Everything downstream of the output gradient is linear in it, so the trunk's gradient is the sum of the two passes'.
 struct TcExternal {
     const float *dout;      // [b][out of head 0] gradient of the loss w.r.t. head 0's outputs (inv_count included); nullptr: discrete loss
-    float critic_weight;    // 1: the critic's SmoothL1 term takes part; 0: its output gradient is zero (second pass)
+    float critic_weight;    // 1: the critic's SmoothL1 term takes part; 0: the critic head is skipped altogether (second pass)
     int zero_off, zero_len; // range of the partial-gradient row that belongs to the head this pass does not touch: written as zeros
 };
 
@@ -463,7 +463,9 @@ __device__ unsigned long long g_tc_span[160 * 8];
 // it.  XR = observation values kept in registers (4 or 8; observ_dim > XR reads the rest on demand).
 // SHARDED: the build with the cross-GPU gradient exchange in its tail (prl_ppo_step_tc_p2p); the single-GPU build leaves that code out
 // (the instruction stream is larger than the instruction cache as it is).
-template <int NA, int XR, bool SHARDED>
+// SKIP1: the second pass of a continuous policy's update (below), where the critic head is left out altogether; a template
+// parameter because even a kernel-uniform runtime flag costs the main build 1.6 % (A/B: registers).
+template <int NA, int XR, bool SHARDED, bool SKIP1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, const float *__restrict__ returns, int64_t b,
@@ -484,6 +486,9 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
     const int O = L.O, A = L.A, nout0 = L.head[0].out;
     TC_STAMP(0);
     TC_SPAN(0);
+    // second pass of a continuous policy's update: the critic contributes nothing (its gradient came from the first pass), so the
+    // whole head - forward, epilogue, dgrad, wgrad - is left out and its partial-gradient entries are written as zeros
+    constexpr bool skip1 = SKIP1;
     if (is_mma_warp) tmem_alloc(&tmem_slot, TM_COLS);   // overlaps the parameter staging of the other warps
     else if (q == 0 && lane == 0) {
         // the first tile's per-row scalars start their way from HBM to L2 while the parameters are staged
@@ -625,7 +630,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             const uint32_t parity = it & 1;
             mma_ok &= mbar_wait(&sbar[0], parity);
             fence_after_sync();
-            if (elect_one()) { issue_forward(D, 0); mma_commit(&bars[0]); issue_forward(D, 1); mma_commit(&bars[5]); }
+            if (elect_one()) { issue_forward(D, 0); mma_commit(&bars[0]); if (!skip1) issue_forward(D, 1); mma_commit(&bars[5]); }
             __syncwarp();
             mma_ok &= mbar_wait(&sbar[1], parity);
             fence_after_sync();
@@ -634,7 +639,13 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
             mma_ok &= mbar_wait(&sbar[2], parity);
             fence_after_sync();
             // the trunk backward needs DF (both dgrads) only: the critic's wgrad gets its own completion barrier
-            if (elect_one()) { issue_head_dgrad(D, 1); mma_commit(&bars[2]); issue_head_wgrad(D, 1, it == 0); mma_commit(&bars[4]); }
+            // (skip1: the commits still mark the completion of the first head's MMAs, which is what the trunk backward waits for)
+            if (elect_one()) {
+                if (!skip1) issue_head_dgrad(D, 1);
+                mma_commit(&bars[2]);
+                if (!skip1) issue_head_wgrad(D, 1, it == 0);
+                mma_commit(&bars[4]);
+            }
             __syncwarp();
             mma_ok &= mbar_wait(&sbar[3], parity);
             fence_after_sync();
@@ -932,7 +943,8 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
                 }
             };
             head(std::integral_constant<int, 0>{});
-            head(std::integral_constant<int, 1>{});
+            if (!skip1) head(std::integral_constant<int, 1>{});
+            else staged(&sbar[2]);   // keep the hand-off (nothing was staged: the MMA warp issues nothing for it)
 
             // ================= trunk backward: DF -> dy0 -> GroupNorm backward -> DZ pieces, tensor-core wgrad against X
             {
@@ -1039,7 +1051,7 @@ k_ppo_grad_tc(const float *__restrict__ params, PolicyLayout L, const float *__r
         for (int idx = tid; idx < HID * HID; idx += TC_COMPUTE) {
             const int j = idx >> 6, k = idx & 63;
             part[L.head[0].w1 + idx] = (it > 0) ? scratch0[j * SS + k] + scratch0[(64 + j) * SS + k] : 0.f;
-            part[L.head[1].w1 + idx] = (it > 0) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f;
+            part[L.head[1].w1 + idx] = (it > 0 && !skip1) ? scratch1[j * SS + k] + scratch1[(64 + j) * SS + k] : 0.f;
         }
         for (int idx = tid; idx < HID * O; idx += TC_COMPUTE) {
             const int j = idx / O, i = idx - j * O;
@@ -1437,13 +1449,17 @@ static int launch_tc(const float *params, const PolicyLayout &L, const float *st
     const bool x4 = obs_dim <= 4;
     int rc;
     if (optp && optp->world > 1)
-        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, true>) : launch(k_ppo_grad_tc<2, 8, true>))
-           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, true>) : launch(k_ppo_grad_tc<4, 8, true>))
-                     : launch(k_ppo_grad_tc<8, 8, true>);
+        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, true, false>) : launch(k_ppo_grad_tc<2, 8, true, false>))
+           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, true, false>) : launch(k_ppo_grad_tc<4, 8, true, false>))
+                     : launch(k_ppo_grad_tc<8, 8, true, false>);
+    else if (ext.dout != nullptr && ext.critic_weight == 0.f)
+        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false, true>) : launch(k_ppo_grad_tc<2, 8, false, true>))
+           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false, true>) : launch(k_ppo_grad_tc<4, 8, false, true>))
+                     : launch(k_ppo_grad_tc<8, 8, false, true>);
     else
-        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false>) : launch(k_ppo_grad_tc<2, 8, false>))
-           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false>) : launch(k_ppo_grad_tc<4, 8, false>))
-                     : launch(k_ppo_grad_tc<8, 8, false>);
+        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false, false>) : launch(k_ppo_grad_tc<2, 8, false, false>))
+           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false, false>) : launch(k_ppo_grad_tc<4, 8, false, false>))
+                     : launch(k_ppo_grad_tc<8, 8, false, false>);
     if (rc != PRL_OK) return rc;
     if (getenv("PRL_TC_TIMING")) {
         long long c[32];
