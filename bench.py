@@ -57,7 +57,8 @@ CONFIGS = {
                note="RND predictor / target MLPs in the path"),
 }
 STATE_BOX = {"CartPole-v1": ([-0.05] * 4, [0.05] * 4), "Pendulum-v1": ([-3.141592653589793, -1.0], [3.141592653589793, 1.0]),
-             "Acrobot-v1": ([-0.1] * 4, [0.1] * 4), "MountainCar-v0": ([-0.6, 0.0], [-0.4, 0.0])}
+             "Acrobot-v1": ([-0.1] * 4, [0.1] * 4), "MountainCar-v0": ([-0.6, 0.0], [-0.4, 0.0]),
+             "MountainCarContinuous-v0": ([-0.6, 0.0, 0.0], [-0.4, 0.0, 0.0])}
 
 
 def parse():

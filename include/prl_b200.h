@@ -28,7 +28,7 @@ extern "C" {
 #define PRL_VERSION 100
 
 enum { PRL_OK = 0, PRL_ERR_INVALID = -1, PRL_ERR_CUDA = -2, PRL_ERR_CAPACITY = -3 };
-enum { PRL_ENV_CARTPOLE = 0, PRL_ENV_PENDULUM = 1, PRL_ENV_ACROBOT = 2, PRL_ENV_MOUNTAINCAR = 3 };
+enum { PRL_ENV_CARTPOLE = 0, PRL_ENV_PENDULUM = 1, PRL_ENV_ACROBOT = 2, PRL_ENV_MOUNTAINCAR = 3, PRL_ENV_MOUNTAINCARCONT = 4 };
 enum { PRL_ACT_I32 = 0, PRL_ACT_I64 = 1, PRL_ACT_F32 = 2 };
 
 const char *prl_last_error(void);

@@ -23,7 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { ORC_CARTPOLE = 0, ORC_PENDULUM = 1, ORC_ACROBOT = 2, ORC_MOUNTAINCAR = 3 };
+enum { ORC_CARTPOLE = 0, ORC_PENDULUM = 1, ORC_ACROBOT = 2, ORC_MOUNTAINCAR = 3, ORC_MOUNTAINCARCONT = 4 };
 
 int orc_env_dims(int env, int *S, int *O, int *A, int *cont, int *max_steps) {
     switch (env) {
@@ -31,6 +31,7 @@ int orc_env_dims(int env, int *S, int *O, int *A, int *cont, int *max_steps) {
     case ORC_PENDULUM: *S = 2; *O = 3; *A = 1; *cont = 1; *max_steps = 200; return 0;
     case ORC_ACROBOT:  *S = 4; *O = 6; *A = 3; *cont = 0; *max_steps = 500; return 0;
     case ORC_MOUNTAINCAR: *S = 2; *O = 2; *A = 3; *cont = 0; *max_steps = 200; return 0;
+    case ORC_MOUNTAINCARCONT: *S = 3; *O = 2; *A = 1; *cont = 1; *max_steps = 999; return 0;
     }
     return -1;
 }
@@ -178,11 +179,70 @@ static int mountaincar_step(double *s, int action, float *obs, double *reward) {
     return position >= goal_position && velocity >= goal_velocity;
 }
 
+/* ---------------------------------------------------------------- MountainCarContinuous-v0 */
+/* gymnasium's continuous_mountain_car.py with numpy's typing spelled out (oracle/envs.py has the story): state = {position,
+ * velocity, stepped}.  stepped == 0: the state is the float64 array reset() made, the step computes in double; afterwards the state
+ * is a float32 array and the step computes in float, with python-float intermediates rounded to float32 where numpy would
+ * (NEP 50).  A clamped force / velocity / position is a python float (a double) again. */
+static void mccont_obs(const double *s, float *o) {
+    o[0] = (float)s[0];
+    o[1] = (float)s[1];
+}
+
+static int mccont_step(double *s, const float *action, float *obs, double *reward) {
+    const int first = s[2] == 0.0;
+    const float a = action[0];
+    /* force = min(max(action[0], -1.0), 1.0): the float32 scalar itself unless it is outside, then the python float bound */
+    int force_py = 0;
+    double force_d = 0.0;
+    float force_f = a;
+    if (-1.0f > a) { force_py = 1; force_d = -1.0; }
+    else if (1.0f < a) { force_py = 1; force_d = 1.0; }
+    /* 3 * position: float64 on the first step, float32 afterwards; math.cos works on the double value of either */
+    const double p3 = first ? 3.0 * s[0] : (double)(3.0f * (float)s[0]);
+    const double t = 0.0025 * cos(p3);                       /* python float */
+    int vel_py = 0, pos_py = 0;                               /* the value is a python float (just clamped) */
+    double vel, pos;
+    if (first) {                                              /* np.float64 arithmetic */
+        const double X = force_py ? force_d * 0.0015 - t : (double)((float)(force_f * 0.0015f) - (float)t);
+        vel = s[1] + X;
+        if (vel > 0.07) { vel = 0.07; vel_py = 1; }
+        if (vel < -0.07) { vel = -0.07; vel_py = 1; }
+        pos = s[0] + vel;
+        if (pos > 0.6) { pos = 0.6; pos_py = 1; }
+        if (pos < -1.2) { pos = -1.2; pos_py = 1; }
+    } else {                                                  /* np.float32 arithmetic */
+        const float X = force_py ? (float)(force_d * 0.0015 - t) : (float)(force_f * 0.0015f) - (float)t;
+        float v = (float)s[1] + X;
+        vel = (double)v;
+        if (v > (float)0.07) { vel = 0.07; vel_py = 1; }
+        if ((vel_py ? (vel < -0.07) : (v < (float)-0.07))) { vel = -0.07; vel_py = 1; }
+        float q = (float)s[0] + (vel_py ? (float)vel : v);
+        pos = (double)q;
+        if (q > (float)0.6) { pos = 0.6; pos_py = 1; }
+        if ((pos_py ? (pos < -1.2) : (q < (float)-1.2))) { pos = -1.2; pos_py = 1; }
+    }
+    /* position == min_position: a python float -1.2 equals itself; a float32 / float64 scalar is compared in its own precision */
+    const int at_min = pos_py ? (pos == -1.2) : (first ? (pos == -1.2) : ((float)pos == (float)-1.2));
+    if (at_min && vel < 0) vel = 0.0;
+    const int over = pos_py ? (pos >= 0.45) : (first ? (pos >= 0.45) : ((float)pos >= (float)0.45));
+    const int terminated = over && vel >= 0.0;
+    double r = terminated ? 100.0 : 0.0;
+    r -= pow((double)a, 2.0) * 0.1;
+    s[0] = (double)(float)pos;                                /* self.state = np.array([position, velocity], dtype=np.float32) */
+    s[1] = (double)(float)vel;
+    s[2] = 1.0;
+    mccont_obs(s, obs);
+    *reward = r;
+    return terminated;
+}
+
 /* ---------------------------------------------------------------- dispatch */
 void orc_env_obs(int env, const double *state, float *obs) {
     if (env == ORC_CARTPOLE) cartpole_obs(state, obs);
     else if (env == ORC_PENDULUM) pendulum_obs(state, obs);
     else if (env == ORC_MOUNTAINCAR) mountaincar_obs(state, obs);
+    else if (env == ORC_MOUNTAINCARCONT) mccont_obs(state, obs);
     else acrobot_obs(state, obs);
 }
 
@@ -191,6 +251,7 @@ int orc_env_step(int env, double *state, const void *action, float *obs, double 
     if (env == ORC_CARTPOLE) return cartpole_step(state, *(const int32_t *)action, obs, reward);
     if (env == ORC_PENDULUM) return pendulum_step(state, (const float *)action, obs, reward);
     if (env == ORC_MOUNTAINCAR) return mountaincar_step(state, *(const int32_t *)action, obs, reward);
+    if (env == ORC_MOUNTAINCARCONT) return mccont_step(state, (const float *)action, obs, reward);
     return acrobot_step(state, *(const int32_t *)action, obs, reward);
 }
 

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
-ENV_CODES = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3}
+ENV_CODES = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3, "MountainCarContinuous-v0": 4}
 
 
 def build(force: bool = False) -> str:
@@ -73,6 +73,9 @@ def rollout(env_id: str, init_state: np.ndarray, tape: np.ndarray, max_steps: in
     AS = d["A"] if d["continuous"] else 1
     cap = E * max_steps
     init_state = np.ascontiguousarray(init_state, np.float64)
+    width = init_state.shape[1]
+    if width < d["S"]:   # MountainCarContinuous: {position, velocity} + the "stepped" flag the C statement keeps (0 after reset)
+        init_state = np.ascontiguousarray(np.concatenate([init_state, np.zeros((E, d["S"] - width))], 1))
     tape = np.ascontiguousarray(tape, np.float32 if d["continuous"] else np.int32)
     assert tape.shape[0] >= max_steps and tape.shape[1] == E
     fs = np.empty((cap, d["O"]), np.float32)
@@ -86,7 +89,7 @@ def rollout(env_id: str, init_state: np.ndarray, tape: np.ndarray, max_steps: in
                           _p(fd), _p(lens), _p(fin), C.byref(rs))
     assert n >= 0
     fa = fa[:n] if d["continuous"] else fa[:n, 0]
-    return dict(states=fs[:n], actions=fa, rewards=fr[:n], dones=fd[:n], lengths=lens, final_state=fin,
+    return dict(states=fs[:n], actions=fa, rewards=fr[:n], dones=fd[:n], lengths=lens, final_state=fin[:, :width],
                 reward_sum=rs.value, N=int(n))
 
 

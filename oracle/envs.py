@@ -9,6 +9,7 @@ This file restates its *published* classic-control algorithms from memory:
   gymnasium/envs/classic_control/pendulum.py   (PendulumEnv.step/reset, angle_normalize)
   gymnasium/envs/classic_control/acrobot.py    (AcrobotEnv.step/_dsdt, rk4, wrap, bound)
   gymnasium/envs/classic_control/mountain_car.py (MountainCarEnv.step/reset)
+  gymnasium/envs/classic_control/continuous_mountain_car.py (Continuous_MountainCarEnv.step/reset)
   gymnasium/wrappers/common.py                 (TimeLimit)
 
 PARITY UNPINNED against gymnasium itself: there is no gymnasium source, wheel or golden vector to
@@ -30,7 +31,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-__all__ = ["make", "CartPole", "Pendulum", "Acrobot", "MountainCar", "ENV_IDS"]
+__all__ = ["make", "CartPole", "Pendulum", "Acrobot", "MountainCar", "MountainCarContinuous", "ENV_IDS"]
 
 
 class _Space(SimpleNamespace):
@@ -315,7 +316,64 @@ class MountainCar(_BaseEnv):
         return self._obs(), reward, terminated
 
 
-ENV_IDS = {"CartPole-v1": CartPole, "Pendulum-v1": Pendulum, "Acrobot-v1": Acrobot, "MountainCar-v0": MountainCar}
+class MountainCarContinuous(_BaseEnv):
+    """gymnasium/envs/classic_control/continuous_mountain_car.py::Continuous_MountainCarEnv (restated from memory, like the others).
+
+    What makes this one delicate is typing, not physics: reset() leaves `self.state` a FLOAT64 array ([uniform draw, 0]), step()
+    leaves it a FLOAT32 array, the action arrives as a float32 array and the constants are python floats - so under NEP 50 the
+    first step of an episode computes in float64 and every later one in float32, `0.0025 * math.cos(...)` is a python float that is
+    rounded to float32 before the subtraction, and a clamped velocity / position / force is a python float again.  Writing the
+    arithmetic with the same objects gymnasium uses reproduces all of that by construction."""
+
+    env_id = "MountainCarContinuous-v0"
+    default_max_episode_steps = 999
+
+    def __init__(self, max_episode_steps=None, goal_velocity=0):
+        super().__init__(max_episode_steps)
+        self.min_action = -1.0
+        self.max_action = 1.0
+        self.min_position = -1.2
+        self.max_position = 0.6
+        self.max_speed = 0.07
+        self.goal_position = 0.45
+        self.goal_velocity = goal_velocity
+        self.power = 0.0015
+        self.observation_space = _Space(shape=(2,), dtype=np.float32)
+        self.action_space = _Space(shape=(1,), dtype=np.float32, low=-1.0, high=1.0)
+
+    def _draw_state(self):
+        return np.array([self.np_random.uniform(low=-0.6, high=-0.4), 0])
+
+    def _obs(self):
+        return np.array(self.state, dtype=np.float32)
+
+    def _physics(self, action):
+        position = self.state[0]
+        velocity = self.state[1]
+        force = min(max(action[0], self.min_action), self.max_action)
+        velocity += force * self.power - 0.0025 * math.cos(3 * position)
+        if velocity > self.max_speed:
+            velocity = self.max_speed
+        if velocity < -self.max_speed:
+            velocity = -self.max_speed
+        position += velocity
+        if position > self.max_position:
+            position = self.max_position
+        if position < self.min_position:
+            position = self.min_position
+        if position == self.min_position and velocity < 0:
+            velocity = 0
+        terminated = bool(position >= self.goal_position and velocity >= self.goal_velocity)
+        reward = 0
+        if terminated:
+            reward = 100.0
+        reward -= math.pow(action[0], 2) * 0.1
+        self.state = np.array([position, velocity], dtype=np.float32)
+        return self.state, reward, terminated
+
+
+ENV_IDS = {"CartPole-v1": CartPole, "Pendulum-v1": Pendulum, "Acrobot-v1": Acrobot, "MountainCar-v0": MountainCar,
+           "MountainCarContinuous-v0": MountainCarContinuous}
 
 
 def make(env_id: str, max_episode_steps: int | None = None):

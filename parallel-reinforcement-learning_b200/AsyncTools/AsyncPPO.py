@@ -203,6 +203,9 @@ class EnvVectorizer:
         if isinstance(states, np.ndarray):
             states = t.from_numpy(np.ascontiguousarray(states, dtype=np.float64))
         s = states.to(device=self.device, dtype=t.float64, non_blocking=True).contiguous()
+        S = self.sim.info["S"]
+        if s.dim() == 2 and s.shape[1] < S:   # trailing bookkeeping components (MountainCarContinuous' "stepped" flag) start at 0, as after reset()
+            s = t.cat([s, t.zeros(s.shape[0], S - s.shape[1], dtype=t.float64, device=self.device)], 1).contiguous()
         return self.sim.set_state(s)
 
     def reset_to(self, states):

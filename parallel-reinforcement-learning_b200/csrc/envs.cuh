@@ -4,7 +4,7 @@
 // Reference call sites: /root/reference/AsyncTools/AsyncPPO.py:53 (env.reset) and :76 (env.step) inside
 // EnvVectorizer; the physics itself is gymnasium==1.1.1 classic_control (third-party):
 //   CartPoleEnv.step  Euler, tau 0.02;  PendulumEnv.step  float32 torque entering fp64;  AcrobotEnv.step  RK4 "book";
-//   MountainCarEnv.step  clipped velocity / position updates.
+//   MountainCarEnv.step  clipped velocity / position updates;  Continuous_MountainCarEnv.step  the same in float32 after the first step.
 #pragma once
 #include "common.cuh"
 #include "pow_glibc.cuh"
@@ -194,6 +194,64 @@ struct MountainCar {
     }
 };
 
+// MountainCarContinuous-v0 (gymnasium/envs/classic_control/continuous_mountain_car.py).  State {position, velocity, stepped}:
+// reset() leaves a FLOAT64 state array, step() a FLOAT32 one, the action is a float32 scalar and the constants are python floats,
+// so (NEP 50) the first step of an episode computes in double and every later one in float, with python-float intermediates
+// rounded to float32 where numpy does it; a clamped force / velocity / position is a python float (a double) again.  Operation
+// by operation the same as oracle/c/prl_oracle.c::mccont_step and oracle/envs.py::MountainCarContinuous.
+struct MountainCarContinuous {
+    static constexpr int ID = PRL_ENV_MOUNTAINCARCONT, S = 3, O = 2, A = 1, AS = 1, MAX_STEPS = 999;
+    static constexpr bool CONT = true;
+    using Action = float;
+    __host__ __device__ static constexpr double reset_hi(int) { return -0.4; }   // reset: position U(-0.6, -0.4), velocity 0, stepped 0
+    __host__ __device__ static constexpr double reset_lo(int) { return -0.6; }
+    static constexpr bool RESET_F32 = false;
+    static constexpr int RESET_DRAWS = 1;
+
+    __device__ static __forceinline__ void obs(const double (&s)[S], float (&o)[O]) {
+        o[0] = (float)s[0];
+        o[1] = (float)s[1];
+    }
+    __device__ static __forceinline__ bool step(double (&s)[S], float a, double &reward) {
+        const bool first = s[2] == 0.0;
+        // force = min(max(action[0], -1.0), 1.0): the float32 scalar unless it lies outside, then the python-float bound
+        const bool force_py = (-1.0f > a) || (1.0f < a);
+        const double force_d = (-1.0f > a) ? -1.0 : 1.0;
+        const double p3 = first ? dmul(3.0, s[0]) : (double)__fmul_rn(3.0f, (float)s[0]);
+        const double t = dmul(0.0025, cos_glibc(p3));                                   // python float
+        bool vel_py = false, pos_py = false;                                            // the value is a python float (just clamped)
+        double vel, pos;
+        if (first) {                                                                    // np.float64 arithmetic
+            const double X = force_py ? dsub(dmul(force_d, 0.0015), t) : (double)__fsub_rn(__fmul_rn(a, 0.0015f), (float)t);
+            vel = dadd(s[1], X);
+            if (vel > 0.07) { vel = 0.07; vel_py = true; }
+            if (vel < -0.07) { vel = -0.07; vel_py = true; }
+            pos = dadd(s[0], vel);
+            if (pos > 0.6) { pos = 0.6; pos_py = true; }
+            if (pos < -1.2) { pos = -1.2; pos_py = true; }
+        } else {                                                                        // np.float32 arithmetic
+            const float X = force_py ? (float)dsub(dmul(force_d, 0.0015), t) : __fsub_rn(__fmul_rn(a, 0.0015f), (float)t);
+            const float v = __fadd_rn((float)s[1], X);
+            vel = (double)v;
+            if (v > (float)0.07) { vel = 0.07; vel_py = true; }
+            if (vel_py ? (vel < -0.07) : (v < (float)-0.07)) { vel = -0.07; vel_py = true; }
+            const float q = __fadd_rn((float)s[0], vel_py ? (float)vel : v);
+            pos = (double)q;
+            if (q > (float)0.6) { pos = 0.6; pos_py = true; }
+            if (pos_py ? (pos < -1.2) : (q < (float)-1.2)) { pos = -1.2; pos_py = true; }
+        }
+        const bool at_min = (pos_py || first) ? (pos == -1.2) : ((float)pos == (float)-1.2);
+        if (at_min && vel < 0) vel = 0.0;
+        const bool over = (pos_py || first) ? (pos >= 0.45) : ((float)pos >= (float)0.45);
+        const bool terminated = over && vel >= 0.0;
+        reward = dsub(terminated ? 100.0 : 0.0, dmul(pow2_glibc((double)a), 0.1));      // reward -= math.pow(action[0], 2) * 0.1
+        s[0] = (double)(float)pos;                                                      // np.array([position, velocity], dtype=np.float32)
+        s[1] = (double)(float)vel;
+        s[2] = 1.0;
+        return terminated;
+    }
+};
+
 // dispatch a functor templated on the env type
 template <typename F>
 inline int dispatch_env(int env_id, F &&f) {
@@ -202,6 +260,7 @@ inline int dispatch_env(int env_id, F &&f) {
         case PRL_ENV_PENDULUM: return f(Pendulum{});
         case PRL_ENV_ACROBOT: return f(Acrobot{});
         case PRL_ENV_MOUNTAINCAR: return f(MountainCar{});
+        case PRL_ENV_MOUNTAINCARCONT: return f(MountainCarContinuous{});
     }
     set_error("unknown env id %d", env_id);
     return PRL_ERR_INVALID;

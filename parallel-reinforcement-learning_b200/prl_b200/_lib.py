@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PRL_B200_LIB") or os.path.join(_HERE, "libprl_b200.so")   # (PRL_B200_LIB: A/B experiments with another build)
 TEST_LIB_PATH = os.path.join(_HERE, "libprl_b200_test.so")
 
-ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3}
+ENV_IDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "Acrobot-v1": 2, "MountainCar-v0": 3, "MountainCarContinuous-v0": 4}
 ACT_I32, ACT_I64, ACT_F32 = 0, 1, 2
 
 _vp, _i32, _i64, _u64, _u32, _f32, _f64, _sz = (C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_float,

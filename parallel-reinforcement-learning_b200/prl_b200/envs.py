@@ -13,6 +13,8 @@ _SPECS = {
     "Pendulum-v1": dict(S=2, O=3, A=1, continuous=True, max_steps=200),
     "Acrobot-v1": dict(S=4, O=6, A=3, continuous=False, max_steps=500),
     "MountainCar-v0": dict(S=2, O=2, A=3, continuous=False, max_steps=200),
+    # state = {position, velocity, stepped}: gymnasium's state array is float64 until the first step and float32 afterwards
+    "MountainCarContinuous-v0": dict(S=3, O=2, A=1, continuous=True, max_steps=999, low=-1.0, high=1.0),
 }
 
 
@@ -28,7 +30,7 @@ class EnvDescriptor:
         self.spec = SimpleNamespace(id=env_id, max_episode_steps=self.max_episode_steps)
         self.observation_space = SimpleNamespace(shape=(s["O"],), dtype=np.float32)
         if s["continuous"]:
-            self.action_space = SimpleNamespace(shape=(s["A"],), dtype=np.float32, low=-2.0, high=2.0)
+            self.action_space = SimpleNamespace(shape=(s["A"],), dtype=np.float32, low=s.get("low", -2.0), high=s.get("high", 2.0))
         else:
             self.action_space = SimpleNamespace(n=s["A"], shape=(), dtype=np.int64)
         self.is_continuous = s["continuous"]

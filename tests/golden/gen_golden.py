@@ -77,6 +77,8 @@ def initial_states(env_id, E, rng):
     if env_id == "Pendulum-v1":
         hi = np.array([np.pi, 1.0])
         return rng.uniform(-hi, hi, size=(E, 2))
+    if env_id == "MountainCarContinuous-v0":   # (float64 start states, as reset() leaves them: the first step computes in double)
+        return rng.uniform([-1.2, -0.07], [0.5, 0.07], size=(E, 2))
     if env_id == "MountainCar-v0":   # wider than gymnasium's reset (-0.6..-0.4, 0) so that goals and the left wall are reached
         return rng.uniform([-1.2, -0.07], [0.55, 0.07], size=(E, 2))
     return rng.uniform(-0.1, 0.1, size=(E, 4)).astype(np.float32).astype(np.float64)
@@ -85,6 +87,8 @@ def initial_states(env_id, E, rng):
 def make_tape(env_id, T, E, rng):
     if env_id == "Pendulum-v1":
         return (2.0 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
+    if env_id == "MountainCarContinuous-v0":   # |a| up to 1.6: the force clamp (python-float branch) is exercised
+        return (1.6 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
     n = 2 if env_id == "CartPole-v1" else 3
     return rng.integers(0, n, size=(T, E)).astype(np.int64)
 
@@ -264,6 +268,11 @@ def main():
         v = gen_rollout(ref_async, "MountainCar-v0", E=16, T=60, seed=14)
         np.savez_compressed(os.path.join(HERE, "rollout_mountaincar.npz"), **v)
         print("mountaincar N =", len(v["states"]), "steps", v["nsteps"], "reward", float(v["reward_score"]), "goals", int((v["dones"] > 0).sum()))
+        return
+    if "--only-mountaincarcont" in sys.argv:   # added in round 2
+        v = gen_rollout(ref_async, "MountainCarContinuous-v0", E=24, T=120, seed=15)
+        np.savez_compressed(os.path.join(HERE, "rollout_mountaincarcont.npz"), **v)
+        print("mountaincarcont N =", len(v["states"]), "steps", v["nsteps"], "reward", float(v["reward_score"]), "episode ends", int((v["dones"] > 0).sum()))
         return
     rolls = {
         "cartpole": gen_rollout(ref_async, "CartPole-v1", E=12, T=40, seed=11),

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 from oracle import cref, ppo as oppo  # noqa: E402
 
-ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0"}
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0",
+        "mountaincarcont": "MountainCarContinuous-v0"}
 
 
 @pytest.fixture(scope="module")
@@ -96,6 +97,9 @@ def run_taped_rollout(ops, env_id, init_state, tape, T):
     info_env = ops.EnvState(env_id, E, T)
     info = info_env.info
     aw = info["A"] if info["continuous"] else 1
+    if init_state.shape[1] < info["S"]:   # MountainCarContinuous: {position, velocity} + the "stepped" flag (0 after reset)
+        init_state = np.concatenate([init_state, np.zeros((E, info["S"] - init_state.shape[1]))], 1)
+    width = init_state.shape[1] if env_id != "MountainCarContinuous-v0" else 2
     info_env.set_state(dev(init_state))
     buf = ops.RolloutBuffer(E, T, info["O"], aw)
     scores = t.zeros(2, dtype=t.float64, device="cuda")
@@ -110,7 +114,7 @@ def run_taped_rollout(ops, env_id, init_state, tape, T):
     N = int(total.item())
     assert int(buf.lengths.sum().item()) == 0  # buffer.clear()
     return dict(N=N, states=ms[:N].cpu().numpy(), actions=ma[:N].cpu().numpy(), rewards=mr[:N].cpu().numpy(),
-                dones=md[:N].cpu().numpy(), lengths=lengths.cpu().numpy(), final_state=info_env.get_state().cpu().numpy(),
+                dones=md[:N].cpu().numpy(), lengths=lengths.cpu().numpy(), final_state=info_env.get_state().cpu().numpy()[:, :width],
                 scores=scores.cpu().numpy(), terminal=info_env.terminal.cpu().numpy())
 
 
@@ -128,6 +132,7 @@ NP_RESET = {
     "Pendulum-v1": lambda g: g.uniform(low=-np.array([np.pi, 1.0]), high=np.array([np.pi, 1.0])),
     "Acrobot-v1": lambda g: g.uniform(low=-0.1, high=0.1, size=(4,)).astype(np.float32).astype(np.float64),
     "MountainCar-v0": lambda g: np.array([g.uniform(low=-0.6, high=-0.4), 0.0]),
+    "MountainCarContinuous-v0": lambda g: np.array([g.uniform(low=-0.6, high=-0.4), 0.0, 0.0]),
 }
 
 
@@ -171,7 +176,8 @@ def test_fused_rollout_matches_reference_worker_golden(ops, golden, key):
     assert r["scores"][0] == pytest.approx(float(g["reward_score"]), rel=1e-12)
 
 
-@pytest.mark.parametrize("key,E,T", [("cartpole", 4096, 128), ("pendulum", 2048, 200), ("acrobot", 1024, 120), ("mountaincar", 4096, 200)])
+@pytest.mark.parametrize("key,E,T", [("cartpole", 4096, 128), ("pendulum", 2048, 200), ("acrobot", 1024, 120), ("mountaincar", 4096, 200),
+                                     ("mountaincarcont", 4096, 300)])
 def test_fused_rollout_matches_c_oracle(ops, key, E, T):
     env_id = ENVS[key]
     rng = np.random.default_rng(42)
@@ -180,6 +186,8 @@ def test_fused_rollout_matches_c_oracle(ops, key, E, T):
         s0 = rng.uniform(-0.05, 0.05, (E, 4)); tape = rng.integers(0, 2, (T, E)).astype(np.int32)
     elif key == "pendulum":
         s0 = rng.uniform([-np.pi, -1], [np.pi, 1], (E, 2)); tape = (2 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
+    elif key == "mountaincarcont":   # float64 start states (what reset() leaves), actions beyond the force clamp, goals and the left wall
+        s0 = rng.uniform([-1.2, -0.07], [0.5, 0.07], (E, 2)); tape = (1.6 * np.tanh(rng.standard_normal((T, E, 1)))).astype(np.float32)
     elif key == "mountaincar":   # start states over the whole track so that goals and the left wall are hit
         s0 = rng.uniform([-1.2, -0.07], [0.55, 0.07], (E, 2)); tape = rng.integers(0, 3, (T, E)).astype(np.int32)
     else:
@@ -193,7 +201,7 @@ def test_fused_rollout_matches_c_oracle(ops, key, E, T):
     assert np.array_equal(bits(got["actions"].reshape(want["actions"].shape)), bits(want["actions"]))
 
 
-@pytest.mark.parametrize("key,horizon", [("cartpole", 40), ("pendulum", 25), ("acrobot", 30), ("mountaincar", 35)])
+@pytest.mark.parametrize("key,horizon", [("cartpole", 40), ("pendulum", 25), ("acrobot", 30), ("mountaincar", 35), ("mountaincarcont", 30)])
 def test_auto_reset_rollout_matches_oracle_episodes(ops, key, horizon):
     """Opt-in auto-reset (north_star; NOT the reference's worker): every env fills all T slots, an env whose episode ends is reset
     in place.  Checked against the oracle run episode by episode: env e's k-th episode starts from what prl_env_reset draws in

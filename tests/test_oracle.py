@@ -6,7 +6,8 @@ import torch as t
 
 from oracle import cref, envs as oenvs, ppo as oppo, vec as ovec
 
-ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0"}
+ENVS = {"cartpole": "CartPole-v1", "pendulum": "Pendulum-v1", "acrobot": "Acrobot-v1", "mountaincar": "MountainCar-v0",
+        "mountaincarcont": "MountainCarContinuous-v0"}
 
 
 def bits(a):
@@ -62,13 +63,14 @@ def test_c_env_step_equals_numpy_env_step(env_id):
     for ep in range(30):
         e = oenvs.make(env_id, max_episode_steps=150)
         e.reset(seed=100 + ep)
-        st = np.array(e.state, np.float64).copy()
+        st = np.zeros(d["S"])                      # (MountainCarContinuous: + the "stepped" flag of the C statement, 0 after reset)
+        st[: len(e.state)] = np.array(e.state, np.float64)
         while True:
             a = (2.6 * np.tanh(rng.standard_normal(1))).astype(np.float32) if d["continuous"] else int(rng.integers(0, d["A"]))
             o, r, term, trunc, _ = e.step(a)
             o2, r2, term2 = cref.env_step(env_id, st, a)
             assert np.array_equal(bits(o), bits(o2)) and np.float64(r).tobytes() == np.float64(r2).tobytes()
-            assert term == term2 and np.array_equal(bits(np.asarray(e.state, np.float64)), bits(st))
+            assert term == term2 and np.array_equal(bits(np.asarray(e.state, np.float64)), bits(st[: len(e.state)]))
             n += 1
             if term or trunc:
                 break
