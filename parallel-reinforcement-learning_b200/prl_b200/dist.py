@@ -75,10 +75,14 @@ def init_from_env(backend: str | None = None) -> Comm | None:
         _ACTIVE = None
         return None
     if not td.is_initialized():
+        # PRL_SAME_DEVICE_PEERS=1 (tests only): every rank runs on GPU 0 - two processes time-slicing one device, gloo for the
+        # collectives (NCCL refuses two ranks on one GPU), CUDA IPC for the exchange buffers.  It lets a 1-GPU box exercise the
+        # sharded update end to end; each cross-rank wait then costs a context time slice, so it is no way to run anything else.
+        same = os.environ.get("PRL_SAME_DEVICE_PEERS") == "1"
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            backend = os.environ.get("PRL_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() and not same else "gloo")
         if torch.cuda.is_available():
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            torch.cuda.set_device(0 if same else int(os.environ.get("LOCAL_RANK", "0")))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         td.init_process_group(backend=backend)
     _ACTIVE = Comm()
@@ -111,7 +115,8 @@ def peer_access_possible(comm: Comm) -> bool:
 
     dev = torch.cuda.current_device()
     info = comm.allgather_obj((socket.gethostname(), dev))
-    ok = len({h for h, _ in info}) == 1 and len({d for _, d in info}) == len(info)
+    same = os.environ.get("PRL_SAME_DEVICE_PEERS") == "1"   # (tests only: see init_from_env)
+    ok = len({h for h, _ in info}) == 1 and (same or len({d for _, d in info}) == len(info))
     if ok:
         ok = all(d == dev or torch.cuda.can_device_access_peer(dev, d) for _, d in info)
     return all(comm.allgather_obj(bool(ok)))

@@ -19,6 +19,14 @@ rank = comm.rank
 env = make("CartPole-v1")
 
 
+def gather2(x):
+    """[rank 0's x, rank 1's x] on the host (through the CPU, so that it also works over gloo when both ranks share one GPU)."""
+    both = [None, None]
+    t.distributed.all_gather_object(both, x.detach().cpu())
+    return both
+
+
+
 def run(peer_exchange, graph, envs):
     t.manual_seed(1234)
     ppo = PPO(is_continuous=False, observ_dim=4, action_dim=2, lr=3e-4, k_epochs=3, mini_batch_size=1024, batch_size=256, use_RND=False)
@@ -40,8 +48,7 @@ for graph in (False, True):
     d = (got - ref).abs().max().item()
     # rank-order summation of two addends is commutative, so the exchange is bit-identical to NCCL's sum
     assert d == 0.0, f"rank {rank} graph={graph}: peer-exchange weights differ from NCCL path by {d}"
-    both = [t.empty_like(got) for _ in range(2)]
-    t.distributed.all_gather(both, got)
+    both = gather2(got)
     assert t.equal(both[0], both[1]), "ranks diverged"
 # Acrobot + RND, sharded: the predictor update allreduces its re-weighted gradient, so the replicas stay identical
 t.manual_seed(7)
@@ -54,8 +61,7 @@ a.worker()
 ppo.learn()
 t.cuda.synchronize()
 for flat in (ppo.rnd.pred_flat, ppo.policy.flat):
-    both = [t.empty_like(flat) for _ in range(2)]
-    t.distributed.all_gather(both, flat.contiguous())
+    both = gather2(flat)
     assert t.equal(both[0], both[1]), "RND run: ranks diverged"
 assert not t.equal(pred0, ppo.rnd.pred_flat) and t.isfinite(ppo.rnd.pred_flat).all()
 
@@ -93,8 +99,7 @@ ok = d <= 1e-5 * np.abs(want) + 2e-6
 print(f"[parity] rank {rank}: sharded learn() ({sum(n_all)} rows on 2 ranks as {n_all}, {2 * n_mb} optimiser steps, in-kernel peer exchange) vs oracle.ppo.learn "
       f"fed the union-of-k-th-chunks schedule: {100 * ok.mean():.2f} % within 1e-5*|w| + 2e-6, max |diff| {d.max():.2e}", flush=True)
 assert ok.mean() >= 0.9995 and d.max() <= 1e-5, (ok.mean(), d.max())   # achieved 99.99 %, 4.1e-6
-both = [t.empty_like(ppo.policy.flat) for _ in range(2)]
-t.distributed.all_gather(both, ppo.policy.flat.contiguous())
+both = gather2(ppo.policy.flat)
 assert t.equal(both[0], both[1]), "H7 run: ranks diverged"
 ppo.close()
 open(os.path.join(out, f"rank{rank}"), "w").write("ok")
