@@ -130,11 +130,16 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
  * auto_reset_horizon > 0 (opt-in; 0 = the reference's worker, where a finished env drops out - AsyncPPO.py:118,143-146):
  * an env whose episode ends - terminated, or auto_reset_horizon (= the TimeLimit) steps into the episode - is reset in
  * place (its k-th reset draws what prl_env_reset draws in episode `episode | k << 40`) and keeps stepping, so every env
- * fills all T_cap slots; the last slot closes the running episode with done = 1.  lengths[e] = T_cap. */
+ * fills all T_cap slots; the last slot closes the running episode with done = 1.  lengths[e] = T_cap.
+ * score_ws != NULL (prl_rollout_score_ws_doubles(E) doubles, zeroed once): the reward sum is accumulated in a fixed order
+ * (per-CTA partials, added in CTA order by the last CTA to finish) and is bit-reproducible; NULL: double atomicAdd. */
 int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed,
                      uint64_t episode, const void *tape, double *state, int32_t *elapsed, uint8_t *terminal,
                      float *buf_states, float *buf_actions, float *buf_rewards, float *buf_dones, float *buf_logp,
-                     float *buf_values, int32_t *lengths, double *scores, int auto_reset_horizon, void *stream);
+                     float *buf_values, int32_t *lengths, double *scores, int auto_reset_horizon, double *score_ws,
+                     void *stream);
+/* doubles of score_ws for E envs (prl_rollout_eval; zeroed once by the caller) */
+size_t prl_rollout_score_ws_doubles(int E);
 
 /* ---------------------------------------------------------------- PPO.compute_gae (PPO/PPO.py:107-120) */
 /* Flat reverse scan over the env-major buffer, float32, same operation order as the reference;

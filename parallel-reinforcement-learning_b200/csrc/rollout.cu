@@ -440,7 +440,7 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
           uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
           uint8_t *__restrict__ terminal, float *__restrict__ bs, float *__restrict__ ba, float *__restrict__ br,
           float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores, float *__restrict__ blp,
-          float *__restrict__ bv, int horizon) {
+          float *__restrict__ bv, int horizon, double *__restrict__ score_ws) {
     extern __shared__ __align__(16) float smem[];
     constexpr int NT = TAPED ? TPB : EV_THREADS;
     EvSmem S{};
@@ -549,8 +549,25 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
     const double bsum = block_sum<double>(rsum, red);
     const double blen = block_sum<double>((double)len, red);
     if (threadIdx.x == 0) {
-        atomicAdd(scores + 0, bsum);
-        atomicAdd(scores + 1, blen);
+        if (score_ws == nullptr) {   // order-dependent in the last bits of the reward sum (the step count is exact either way)
+            atomicAdd(scores + 0, bsum);
+            atomicAdd(scores + 1, blen);
+        } else {
+            // bit-reproducible: every CTA leaves its partial sums, the one that draws the last ticket adds them in CTA order
+            // score_ws = {ticket (8 bytes), partial[grid][2]}, zero ticket on entry and on exit
+            score_ws[2 + 2 * blockIdx.x] = bsum;
+            score_ws[3 + 2 * blockIdx.x] = blen;
+            __threadfence();
+            unsigned int *ticket = reinterpret_cast<unsigned int *>(score_ws);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+                __threadfence();
+                double a = 0.0, b = 0.0;
+                for (unsigned int c = 0; c < gridDim.x; ++c) { a += __ldcg(score_ws + 2 + 2 * c); b += __ldcg(score_ws + 3 + 2 * c); }
+                scores[0] += a;
+                scores[1] += b;
+                *ticket = 0u;
+            }
+        }
     }
 }
 
@@ -755,13 +772,15 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
                 const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
                 float *buf_rewards, float *buf_dones, int32_t *lengths, double *scores, void *stream) {
     return prl_rollout_eval(env_id, E, T_cap, params, action_scaling, seed, episode, tape, state, elapsed, terminal, buf_states, buf_actions,
-                            buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, 0, stream);
+                            buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, 0, nullptr, stream);
 }
+
+size_t prl_rollout_score_ws_doubles(int E) { return 2 + 2 * (size_t)cdiv(E > 0 ? E : 1, TPB < EV_ROWS ? TPB : EV_ROWS); }
 
 int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
                      const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
                      float *buf_rewards, float *buf_dones, float *buf_logp, float *buf_values, int32_t *lengths, double *scores,
-                     int auto_reset_horizon, void *stream) {
+                     int auto_reset_horizon, double *score_ws, void *stream) {
     PRL_REQUIRE(E > 0 && T_cap > 0 && state && elapsed && terminal && buf_states && buf_actions && buf_rewards && buf_dones &&
                     lengths && scores, "prl_rollout: bad arguments");
     PRL_REQUIRE(tape || params, "prl_rollout: need policy parameters or an action tape");
@@ -775,7 +794,7 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
         if (tape) {
             k_rollout<ENV, true><<<cdiv(E, TPB), TPB, 0, st>>>(E, T_cap, params, L, action_scaling, seed, episode, tape, state, elapsed,
                                                               terminal, buf_states, buf_actions, buf_rewards, buf_dones, lengths, scores,
-                                                              nullptr, nullptr, auto_reset_horizon);
+                                                              nullptr, nullptr, auto_reset_horizon, score_ws);
         } else {
             PRL_REQUIRE(!(buf_logp && ENV::CONT && ENV::A != 1), "prl_rollout_eval: continuous envs with action_dim > 1 are evaluated by prl_policy_evaluate");
             const size_t smem = (size_t)ev_layout(L, buf_logp ? L.n_heads : L.n_heads - 1).total * sizeof(float);
@@ -783,7 +802,7 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
             PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
                                                                  elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
-                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon);
+                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);
         }
         return check_launch("k_rollout");
     });

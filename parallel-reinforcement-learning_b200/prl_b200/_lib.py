@@ -47,7 +47,8 @@ PROTOTYPES = {
     "prl_policy_act": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "prl_policy_evaluate": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "prl_rollout": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "prl_rollout_eval": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64] + [_vp] * 12 + [_i32, _vp]),
+    "prl_rollout_eval": (_i32, [_i32, _i32, _i32, _vp, _f32, _u64, _u64] + [_vp] * 12 + [_i32, _vp, _vp]),
+    "prl_rollout_score_ws_doubles": (_sz, [_i32]),
     "prl_gae": (_i32, [_vp, _vp, _vp, _vp, _f64, _f64, _i64, _vp, _vp, _sz, _vp]),
     "prl_gae_ws_bytes": (_sz, [_i64]),
     "prl_gae_columns": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _vp, _vp]),

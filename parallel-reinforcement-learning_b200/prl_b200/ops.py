@@ -249,10 +249,12 @@ def rollout(env: EnvState, buf: RolloutBuffer, params, action_scaling, seed, epi
         buf.want_eval()
     T = buf.T if steps is None else int(steps)
     assert 0 < T <= buf.T
+    if getattr(env, "score_ws", None) is None:   # fixed-order accumulation of the reward sum (bit-reproducible scores)
+        env.score_ws = torch.zeros(int(_lib.fn("prl_rollout_score_ws_doubles")(env.E)), dtype=torch.float64, device=_dev())
     call("prl_rollout_eval", env.code, env.E, T, _ptr(params), float(action_scaling or 1.0), seed, episode, _ptr(tape),
          _ptr(env.state), _ptr(env.elapsed), _ptr(env.terminal), _ptr(buf.states), _ptr(buf.actions), _ptr(buf.rewards),
          _ptr(buf.dones), _ptr(buf.logp) if evaluate else None, _ptr(buf.values) if evaluate else None, _ptr(buf.lengths),
-         _ptr(scores, torch.float64), int(auto_reset_horizon), _stream())
+         _ptr(scores, torch.float64), int(auto_reset_horizon), _ptr(env.score_ws, torch.float64), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ GAE

@@ -402,6 +402,24 @@ def test_batch1_playback_loop_like_test_py(api, key):
     assert len(totals) == 2 and all(np.isfinite(totals))
 
 
+def test_reward_score_is_bit_reproducible(api):
+    """AsyncPPO.reward_score (AsyncPPO.py:131) of the fused worker: the per-CTA reward sums are added in CTA order by the last CTA to
+    finish, not by atomics - the same rollout gives the same bits, and they are the float64 sum of the stored rewards."""
+    A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
+    got = []
+    for _ in range(3):
+        t.manual_seed(21)
+        ppo = P.PPO(is_continuous=True, observ_dim=3, action_dim=1, action_scaling=2.0)
+        ap = A.AsyncPPO.AsyncPPO(env=prl.make("Pendulum-v1", max_episode_steps=40), ppo=ppo, num_envs=5000, steps=1)
+        ap.step_score = 0
+        ap.reward_score = 0
+        ap.worker()
+        rewards = ppo.memory.device_view(3, 1, ppo.device)[2]
+        got.append((np.float64(ap.reward_score).tobytes(), int(ap.step_score), float(rewards.double().sum().item())))
+    assert got[0][0] == got[1][0] == got[2][0] and got[0][1] == 5000 * 40
+    assert np.frombuffer(got[0][0], np.float64)[0] == pytest.approx(got[0][2], rel=1e-6)   # (the stored rewards are float32 copies)
+
+
 def test_reference_unittest_call_patterns(api):
     """The duck-typing the reference's own unittests rely on."""
     A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
