@@ -1417,7 +1417,7 @@ static int launch_tc(const float *params, const PolicyLayout &L, const float *st
     const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
     PRL_REQUIRE(ws_floats >= tc_ws_floats(L, grid), "%s: workspace too small", who);
     PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "%s: workspace must be 16-byte aligned", who);
-    const int NA = action_dim <= 2 ? 2 : action_dim <= 4 ? 4 : 8;
+    const int NA = action_dim <= 2 ? 2 : (action_dim == 3 && obs_dim > 4 && obs_dim <= 6) ? 3 : action_dim <= 4 ? 4 : 8;
     const size_t smem = tc_smem_bytes(L, NA);
     PRL_REQUIRE(smem <= 227 * 1024, "%s: needs %zu B shared memory (> 227 KB)", who, smem);
     PRL_REQUIRE(grid <= TC_MAX_GRID, "%s: grid %d > %d", who, grid, TC_MAX_GRID);
@@ -1446,20 +1446,20 @@ static int launch_tc(const float *params, const PolicyLayout &L, const float *st
                                     loss_partials, status, opt, qpc, ext));
         return PRL_OK;
     };
+    // builds: actor width NA x observation registers XR {(2,4) (2,8) (3,6) (4,4) (4,8) (8,8)} x {single GPU | sharded | second pass of a
+    // continuous update (no critic head)}.  (3,6) exists for Acrobot's shapes (A = 3, O = 6): A/B 66.0 against 69.1 us per launch with (4,8).
     const bool x4 = obs_dim <= 4;
+    const bool v36 = action_dim == 3 && obs_dim > 4 && obs_dim <= 6;
+#define PRL_TC_PICK(SH, SK)                                                                                                \
+    (v36 ? launch(k_ppo_grad_tc<3, 6, SH, SK>)                                                                             \
+     : NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, SH, SK>) : launch(k_ppo_grad_tc<2, 8, SH, SK>))                          \
+     : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, SH, SK>) : launch(k_ppo_grad_tc<4, 8, SH, SK>))                          \
+               : launch(k_ppo_grad_tc<8, 8, SH, SK>))
     int rc;
-    if (optp && optp->world > 1)
-        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, true, false>) : launch(k_ppo_grad_tc<2, 8, true, false>))
-           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, true, false>) : launch(k_ppo_grad_tc<4, 8, true, false>))
-                     : launch(k_ppo_grad_tc<8, 8, true, false>);
-    else if (ext.dout != nullptr && ext.critic_weight == 0.f)
-        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false, true>) : launch(k_ppo_grad_tc<2, 8, false, true>))
-           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false, true>) : launch(k_ppo_grad_tc<4, 8, false, true>))
-                     : launch(k_ppo_grad_tc<8, 8, false, true>);
-    else
-        rc = NA == 2 ? (x4 ? launch(k_ppo_grad_tc<2, 4, false, false>) : launch(k_ppo_grad_tc<2, 8, false, false>))
-           : NA == 4 ? (x4 ? launch(k_ppo_grad_tc<4, 4, false, false>) : launch(k_ppo_grad_tc<4, 8, false, false>))
-                     : launch(k_ppo_grad_tc<8, 8, false, false>);
+    if (optp && optp->world > 1) rc = PRL_TC_PICK(true, false);
+    else if (ext.dout != nullptr && ext.critic_weight == 0.f) rc = PRL_TC_PICK(false, true);
+    else rc = PRL_TC_PICK(false, false);
+#undef PRL_TC_PICK
     if (rc != PRL_OK) return rc;
     if (getenv("PRL_TC_TIMING")) {
         long long c[32];

@@ -8,10 +8,15 @@ from prl_b200 import ops
 path = sys.argv[1] if len(sys.argv) > 1 else "tc"
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-O, A = 4, 2
-g = np.load(os.path.join(ROOT, "tests/golden/learn_discrete.npz"))
+O, A = (int(x) for x in os.environ.get("PRL_PROF_SHAPE", "4,2").split(","))   # observ_dim, action_dim (discrete policy)
 rng = np.random.default_rng(0)
-params = t.from_numpy(g["init_flat"]).cuda()
+if (O, A) == (4, 2):
+    params = t.from_numpy(np.load(os.path.join(ROOT, "tests/golden/learn_discrete.npz"))["init_flat"]).cuda()
+else:   # a freshly initialised reference-style network of that shape
+    sys.path.insert(0, os.path.join(ROOT, "parallel-reinforcement-learning_b200"))
+    from PPO import ActorCritic
+    t.manual_seed(0)
+    params = ActorCritic(False, O, A).flat.detach().clone()
 s = t.from_numpy(rng.uniform(-1, 1, (N, O)).astype(np.float32)).cuda()
 a = t.from_numpy(rng.integers(0, A, (N, 1)).astype(np.float32)).cuda()
 logp, _, _ = ops.policy_evaluate(params, False, O, A, s, a)
