@@ -6,9 +6,10 @@ box) - by this committed recipe, at build() time, into git-ignored directories t
   oracle/_ref/reference/{PPO,AsyncTools}/*.py            the reference's hot path, verbatim - imported behind a stub `gymnasium`
                                                          whose envs are oracle/envs.py by oracle/ref_runner.py (bench.py
                                                          --impl reference, kind "reference")
-  parallel-reinforcement-learning_b200/unittests/*.py    the reference's own unittests, verbatim; each does
-                                                         sys.path.insert(0, <its directory>/..), so sitting next to the drop-in
-                                                         `PPO` / `AsyncTools` packages makes them exercise the B200 build
+  oracle/_ref/dropin/unittests/*.py                      the reference's own unittests, verbatim; each does
+                                                         sys.path.insert(0, <its directory>/..) - an empty directory here - and then
+                                                         imports `PPO` / `AsyncTools`, which PYTHONPATH resolves to the drop-in
+                                                         packages of the B200 build
                                                          (tests/test_gpu_api.py::test_reference_unittests_run_unmodified)
 
 Nothing here is product code and nothing staged is ever committed (.gitignore)."""
@@ -21,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = "/root/reference"
 REF_STAGE = os.path.join(HERE, "_ref", "reference")
-UNITTEST_STAGE = os.path.join(ROOT, "parallel-reinforcement-learning_b200", "unittests")
+UNITTEST_STAGE = os.path.join(HERE, "_ref", "dropin", "unittests")
 PLAN = (("PPO", os.path.join(REF_STAGE, "PPO")), ("AsyncTools", os.path.join(REF_STAGE, "AsyncTools")), ("unittests", UNITTEST_STAGE))
 
 

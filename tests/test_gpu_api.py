@@ -477,20 +477,22 @@ def test_reference_unittest_call_patterns(api):
 
 def test_reference_unittests_run_unmodified(api, capsys):
     """SURVEY.md section 2, component 12: the reference's own unittests/ (test_PPO.py, test_utils.py, test_AsyncPPO.py),
-    byte-identical copies staged at build() time by oracle/stage_reference.py next to the drop-in packages, executed as they
-    are: each file puts its parent directory first on sys.path and imports `PPO` / `AsyncTools` from there - the B200 build.
-    `import gymnasium` is served by tests/stubs/gymnasium (the image has no gymnasium wheel) whose make() is prl_b200.make."""
+    byte-identical copies staged at build() time by oracle/stage_reference.py under oracle/_ref/dropin/unittests/, executed as
+    they are: each file puts its parent directory (empty) first on sys.path and imports `PPO` / `AsyncTools`, which PYTHONPATH
+    resolves to the drop-in packages of the B200 build.  `import gymnasium` is served by tests/stubs/gymnasium (the image has no
+    gymnasium wheel) whose make() is prl_b200.make."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    staged = os.path.join(root, "parallel-reinforcement-learning_b200", "unittests")
+    staged = os.path.join(root, "oracle", "_ref", "dropin", "unittests")
+    pkg = os.path.join(root, "parallel-reinforcement-learning_b200")
     files = sorted(f for f in (os.listdir(staged) if os.path.isdir(staged) else []) if f.startswith("test_") and f.endswith(".py"))
     if not files:
         pytest.skip("the reference's unittests are not staged (build() stages them where /root/reference exists)")
     assert files == ["test_AsyncPPO.py", "test_PPO.py", "test_utils.py"]
-    env = dict(os.environ, PYTHONPATH=os.path.join(root, "tests", "stubs"), PYTHONDONTWRITEBYTECODE="1")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([pkg, os.path.join(root, "tests", "stubs")]), PYTHONDONTWRITEBYTECODE="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", *files], cwd=staged, env=env, capture_output=True,
                        text=True, timeout=900)
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
