@@ -42,9 +42,13 @@ class Comm:
         return out
 
     def allgather_int(self, value: int) -> list[int]:
-        out = [None] * self.world_size
-        td.all_gather_object(out, int(value), group=self.group)
-        return [int(v) for v in out]
+        """One integer per rank.  A tensor all_gather (one small collective) rather than all_gather_object, which pickles and
+        runs two collectives with host synchronisations in between - this sits on the critical path of every sharded learn()."""
+        cuda = td.get_backend(self.group) == "nccl"
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()) if cuda else "cpu")
+        out = torch.empty(self.world_size, dtype=torch.int64, device=mine.device)
+        td.all_gather_into_tensor(out, mine, group=self.group)
+        return [int(v) for v in out.tolist()]
 
     def barrier(self):
         td.barrier(group=self.group)
