@@ -167,8 +167,13 @@ struct HeadCtx {
 
 constexpr int MAX_OUT = 8;  // action_dim supported by the fused update kernel (register-resident head outputs)
 
-// forward of one head for this thread's row: returns outputs, keeps zhat/rstd
-__device__ __forceinline__ void head_forward_row(const HeadCtx &H, const float *Fcol, float *Zcol, float (&zhat)[HID],
+// forward of one head for this thread's row: returns outputs, keeps zhat/rstd.
+// NOT inlined (nor is head_backward_row) since round 2: the fp32-FMA update kernel calls them up to seven times (continuous policy:
+// mu, log_std, mu again, critic) and with everything inlined it was 2.7 MB of SASS that took ptxas 6.3 minutes - most of a clean
+// build().  As calls: 0.9 MB, 35 s; the price is 35 % on this path (1 139 against 730 us per 65 536-row launch), which since round 2
+// is the second implementation the parity tests run next to the tensor-core path and the fallback for policies wider than
+// observ_dim 16 / action_dim 8, not the path any BASELINE configuration takes.
+static __device__ __noinline__ void head_forward_row(const HeadCtx &H, const float *Fcol, float *Zcol, float (&zhat)[HID],
                                                  float (&rstd)[GROUPS], float (&out)[MAX_OUT]) {
     // dot form: z[j] = <f, W1[j][:]> with f in registers; results parked in the Z column
     {
@@ -201,7 +206,7 @@ __device__ __forceinline__ void head_forward_row(const HeadCtx &H, const float *
 // backward of one head.  On entry zhat/rstd hold the forward state of this row, dout its output gradients (zeros for
 // padding rows).  Adds the row's contribution to df (registers) and the tile's contribution to the block partials.
 // Register budget: only zhat[64] and df[64] stay live; dy is recomputed from (zhat, dout) in each staging pass.
-__device__ __forceinline__ void head_backward_row(const HeadCtx &H, const UpSmem &W, const float (&zhat)[HID],
+static __device__ __noinline__ void head_backward_row(const HeadCtx &H, const UpSmem &W, const float (&zhat)[HID],
                                                   const float (&rstd)[GROUPS], const float (&dout)[MAX_OUT], float (&df)[HID]) {
     float *Zcol = W.Z + threadIdx.x, *Dcol = W.D + threadIdx.x;
     auto dy_of = [&](int j) -> float {   // dL/dy_j through Linear(64,out) and SiLU
