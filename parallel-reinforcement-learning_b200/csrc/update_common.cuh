@@ -170,7 +170,8 @@ constexpr int MAX_OUT = 8;  // action_dim supported by the fused update kernel (
 // forward of one head for this thread's row: returns outputs, keeps zhat/rstd.
 // NOT inlined (nor is head_backward_row) since round 2: the fp32-FMA update kernel calls them up to seven times (continuous policy:
 // mu, log_std, mu again, critic) and with everything inlined it was 2.7 MB of SASS that took ptxas 6.3 minutes - most of a clean
-// build().  As calls: 0.9 MB, 35 s; the price is 35 % on this path (1 139 against 730 us per 65 536-row launch), which since round 2
+// build().  As calls: 0.9 MB, 35 s; with dy evaluated once per element (head_backward_row) the path costs 807 us per 65 536-row
+// launch against 730 us fully inlined, and since round 2 it
 // is the second implementation the parity tests run next to the tensor-core path and the fallback for policies wider than
 // observ_dim 16 / action_dim 8, not the path any BASELINE configuration takes.
 static __device__ __noinline__ void head_forward_row(const HeadCtx &H, const float *Fcol, float *Zcol, float (&zhat)[HID],
@@ -205,20 +206,22 @@ static __device__ __noinline__ void head_forward_row(const HeadCtx &H, const flo
 
 // backward of one head.  On entry zhat/rstd hold the forward state of this row, dout its output gradients (zeros for
 // padding rows).  Adds the row's contribution to df (registers) and the tile's contribution to the block partials.
-// Register budget: only zhat[64] and df[64] stay live; dy is recomputed from (zhat, dout) in each staging pass.
+// dy (dL/dy through Linear(64,out) and SiLU) is evaluated ONCE per element into a local array and read by the three staging passes
+// (it used to be recomputed - expf, a division, the dot with dout - in each of them).
 static __device__ __noinline__ void head_backward_row(const HeadCtx &H, const UpSmem &W, const float (&zhat)[HID],
                                                   const float (&rstd)[GROUPS], const float (&dout)[MAX_OUT], float (&df)[HID]) {
     float *Zcol = W.Z + threadIdx.x, *Dcol = W.D + threadIdx.x;
-    auto dy_of = [&](int j) -> float {   // dL/dy_j through Linear(64,out) and SiLU
+    float dy[HID];
+    // (1) stage h and dout -> dW2, db2
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
         float dh = 0.f;
         for (int a = 0; a < H.out; ++a) dh = fmaf(dout[a], H.w2[a * HID + j], dh);
         const float y = fmaf(zhat[j], H.gw[j], H.gb[j]);
         const float sg = 1.0f / (1.0f + expf(-y));
-        return dh * sg * fmaf(y, 1.0f - sg, 1.0f);
-    };
-    // (1) stage h and dout -> dW2, db2
-#pragma unroll
-    for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = silu(fmaf(zhat[j], H.gw[j], H.gb[j]));
+        dy[j] = dh * sg * fmaf(y, 1.0f - sg, 1.0f);
+        Zcol[j * UP_NTP] = silu(y);
+    }
     for (int a = 0; a < H.out; ++a) Dcol[a * UP_NTP] = dout[a];
     __syncthreads();
     coop_outer_small(W.D, H.out, W.Z, HID, H.p_w2);
@@ -226,13 +229,13 @@ static __device__ __noinline__ void head_backward_row(const HeadCtx &H, const Up
     __syncthreads();
     // (2) stage dy * zhat -> dgamma
 #pragma unroll
-    for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy_of(j) * zhat[j];
+    for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy[j] * zhat[j];
     __syncthreads();
     coop_rowsum(W.Z, HID, H.p_gw);
     __syncthreads();
     // (3) stage dy -> dbeta
 #pragma unroll
-    for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy_of(j);
+    for (int j = 0; j < HID; ++j) Zcol[j * UP_NTP] = dy[j];
     __syncthreads();
     coop_rowsum(W.Z, HID, H.p_gb);
     __syncthreads();
@@ -243,7 +246,7 @@ static __device__ __noinline__ void head_backward_row(const HeadCtx &H, const Up
 #pragma unroll
         for (int i = 0; i < GSIZE; ++i) {
             const int j = g * GSIZE + i;
-            d[i] = dy_of(j) * H.gw[j];
+            d[i] = dy[j] * H.gw[j];
             m1 += d[i];
             m2 = fmaf(d[i], zhat[j], m2);
         }
