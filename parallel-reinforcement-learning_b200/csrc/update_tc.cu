@@ -1353,13 +1353,26 @@ static void tc_split(int64_t b, int *grid, int *qpc) {
     const int64_t gr = (nq + q - 1) / q;
     *grid = (int)(gr > 0 ? gr : 1);
 }
+// Fused optimiser step: the tail (slice reduction, squared norm, clip + AdamW) is spread over the CTAs of the launch, one
+// 64-parameter slice after the other per CTA - a small minibatch (512 rows = 4 CTAs) would walk 36 slices per CTA, ~1 us each.
+// So the launch is widened to one CTA per slice plus the leader: the CTAs beyond those that own rows stage nothing but the
+// tail's share (they write an all-zero partial row, which changes no bit of the fixed-order sums: x + 0 = x, and row b stays in
+// reduction slice b % RED_SL whatever the grid is).  configs[0] (mini_batch 512): 66 -> ~30 us per optimiser step.
+static int tc_tail_grid(int grid_rows, int P) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (P + 63) / 64 + 1;
+    const int g = want < sms ? want : sms;
+    return grid_rows > g ? grid_rows : g;
+}
 // upper bound of the grid over every minibatch of at most b rows (the workspace is sized once for the largest one)
-static int tc_grid_max(int64_t b) {
+static int tc_grid_max(int64_t b, int P) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t nt = (b + TC_ROWS - 1) / TC_ROWS;
-    return (int)(nt < sms ? (nt > 0 ? nt : 1) : sms);
+    return tc_tail_grid((int)(nt < sms ? (nt > 0 ? nt : 1) : sms), P);
 }
 // header (4 words: status, arrival counter, unused, launch counter) | partial rows (floats, 16-byte aligned rows) | loss partials
 // (4 doubles per CTA) | squared-norm words (2 tagged 8-byte words per CTA) | clip-coefficient words (2)
@@ -1397,7 +1410,7 @@ static size_t tc_cont_extra_floats(int action_dim, int64_t batch) { return (size
 
 size_t prl_update_tc_ws_floats(int is_continuous, int obs_dim, int action_dim, int64_t batch) {
     const PolicyLayout L = make_policy_layout(is_continuous, obs_dim, action_dim);
-    return tc_ws_floats(L, tc_grid_max(batch)) + (is_continuous ? tc_cont_extra_floats(action_dim, batch) : 0);
+    return tc_ws_floats(L, tc_grid_max(batch, L.total)) + (is_continuous ? tc_cont_extra_floats(action_dim, batch) : 0);
 }
 
 // shared launcher: gradient only (opt == nullptr: + separate reduction kernel) or fused optimiser step
@@ -1414,6 +1427,7 @@ static int launch_tc(const float *params, const PolicyLayout &L, const float *st
                 "%s: policies with observ_dim <= %d and action_dim <= %d only (got O=%d A=%d)", who, TC_MAX_O, TC_MAX_A, obs_dim, action_dim);
     int grid, qpc;
     tc_split(b, &grid, &qpc);
+    if (optp && !getenv("PRL_TC_NARROW_TAIL")) grid = tc_tail_grid(grid, L.total);   // (the variable: A/B against the row CTAs only)
     const int pstride = (L.total + 3) & ~3;   // per-CTA partial rows start 16-byte aligned
     PRL_REQUIRE(ws_floats >= tc_ws_floats(L, grid), "%s: workspace too small", who);
     PRL_REQUIRE(((uintptr_t)ws & 15) == 0, "%s: workspace must be 16-byte aligned", who);
@@ -1502,7 +1516,7 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
     PRL_REQUIRE(prl_ppo_grad_tc_supported(1, obs_dim, action_dim), "%s: observ_dim <= %d and action_dim <= %d only", who, TC_MAX_O, TC_MAX_A);
     PRL_REQUIRE(params && states && actions && old_logp && adv && returns && grad && ws && b > 0, "%s: bad arguments", who);
     const PolicyLayout LC = make_policy_layout(1, obs_dim, action_dim);
-    const size_t base = tc_ws_floats(LC, tc_grid_max(b));
+    const size_t base = tc_ws_floats(LC, tc_grid_max(b, LC.total));
     PRL_REQUIRE(ws_floats >= base + tc_cont_extra_floats(action_dim, b) && ((uintptr_t)ws & 15) == 0, "%s: workspace too small / unaligned", who);
     const size_t off_mu = (base + 3) & ~(size_t)3, off_ls = off_mu + (size_t)action_dim * b, off_pre = (off_ls + (size_t)action_dim * b + 3) & ~(size_t)3;
     float *dmu = ws + off_mu, *dls = ws + off_ls;
