@@ -434,7 +434,10 @@ k_policy_act(const float *__restrict__ params, PolicyLayout L, float action_scal
 // One thread per env for the physics, sampling and bookkeeping; the policy forward of the CTA's 256 envs runs as one
 // register-tiled pass per step (tiled_mlp.cuh) between two barriers.  TAPED: actions come from a tape (teacher forcing,
 // parity tests and the env-step bandwidth benchmark), no network, 128 threads.
-template <class ENV, bool TAPED>
+// RPT (tiled_mlp.cuh): rows per thread of the forward; the CTA holds 32 RPT envs.  8 for throughput; 1 when there are so few envs
+// that the launch cannot fill the GPU anyway (configs[0]: 32 envs) - the 8 warps then share the CTA's 32 rows and a step is
+// several times shorter.  Same bits either way.
+template <class ENV, bool TAPED, int RPT = EV_RPT>
 __global__ void __launch_bounds__(EV_THREADS, 2)
 k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, float action_scaling, uint64_t seed,
           uint64_t episode, const void *__restrict__ tape, double *__restrict__ state, int32_t *__restrict__ elapsed,
@@ -442,7 +445,7 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
           float *__restrict__ bd, int32_t *__restrict__ lengths, double *__restrict__ scores, float *__restrict__ blp,
           float *__restrict__ bv, int horizon, double *__restrict__ score_ws) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int NT = TAPED ? TPB : EV_THREADS;
+    constexpr int NT = TAPED ? TPB : 32 * RPT;   // envs per CTA
     EvSmem S{};
     // blp != nullptr: the old-policy evaluation of PPO.learn (PPO.py:134-154: log-prob of the stored action and V(s) under the
     // acting policy) is taken here, where the network outputs of the step already exist: the critic head joins the forward and two
@@ -454,7 +457,7 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
     }
     __shared__ double red[32];
     const int e = blockIdx.x * NT + threadIdx.x;
-    const bool valid = e < E;
+    const bool valid = (int)threadIdx.x < NT && e < E;
     bool alive = valid;
     double s[ENV::S];
     if (valid) load_state<ENV>(state, E, e, s);
@@ -474,11 +477,13 @@ k_rollout(int E, int T_cap, const float *__restrict__ params, PolicyLayout L, fl
             if (!__any_sync(0xffffffffu, alive)) break;
         } else {
             // the whole CTA runs the forward while any of its envs is alive (finished envs feed zeros, results unused)
-            float *sX = smem + S.x + threadIdx.x * ENV::O;
+            if ((int)threadIdx.x < NT) {
+                float *sX = smem + S.x + threadIdx.x * ENV::O;
 #pragma unroll
-            for (int c = 0; c < ENV::O; ++c) sX[c] = alive ? o[c] : 0.f;
+                for (int c = 0; c < ENV::O; ++c) sX[c] = alive ? o[c] : 0.f;
+            }
             if (!__syncthreads_or(alive)) break;
-            ev_forward_tile(smem, S, L);
+            ev_forward_tile<RPT>(smem, S, L);
             __syncthreads();
         }
         if (alive) {
@@ -775,7 +780,7 @@ int prl_rollout(int env_id, int E, int T_cap, const float *params, float action_
                             buf_rewards, buf_dones, nullptr, nullptr, lengths, scores, 0, nullptr, stream);
 }
 
-size_t prl_rollout_score_ws_doubles(int E) { return 2 + 2 * (size_t)cdiv(E > 0 ? E : 1, TPB < EV_ROWS ? TPB : EV_ROWS); }
+size_t prl_rollout_score_ws_doubles(int E) { return 2 + 2 * (size_t)cdiv(E > 0 ? E : 1, 32); }   // (a CTA holds at least 32 envs)
 
 int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float action_scaling, uint64_t seed, uint64_t episode,
                      const void *tape, double *state, int32_t *elapsed, uint8_t *terminal, float *buf_states, float *buf_actions,
@@ -800,6 +805,17 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
             const size_t smem = (size_t)ev_layout(L, buf_logp ? L.n_heads : L.n_heads - 1).total * sizeof(float);
             PRL_REQUIRE(smem <= 227 * 1024, "prl_rollout_eval: %zu B of shared memory needed (> 227 KB)", smem);
             PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // few envs (at most 32 per CTA slot of the GPU): one row per 8 threads, 32 envs per CTA - see the kernel's header
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const bool few = E <= 32 * 2 * sms && !getenv("PRL_ROLLOUT_RPT8");   // (the variable: A/B against the throughput form)
+            if (few) {
+                PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_rollout<ENV, false, 1><<<cdiv(E, 32), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
+                                                                 elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
+                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);
+            } else
             k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
                                                                  elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
                                                                  lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);

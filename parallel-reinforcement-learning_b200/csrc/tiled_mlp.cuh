@@ -71,12 +71,13 @@ __device__ __forceinline__ void ev_stage_weights(float *smem, const EvSmem &S, c
 }
 
 // GroupNorm (this thread's 8 features = one group) + affine + SiLU on 8 rows; same operation order as gn_silu (mlp.cuh)
-__device__ __forceinline__ void ev_gn_silu(float (&z)[EV_RPT][8], const float *gw_p, const float *gb_p, int fg) {
+template <int RPT>
+__device__ __forceinline__ void ev_gn_silu(float (&z)[RPT][8], const float *gw_p, const float *gb_p, int fg) {
     const float4 ga = *reinterpret_cast<const float4 *>(gw_p + 4 * fg), gb_ = *reinterpret_cast<const float4 *>(gw_p + 32 + 4 * fg);
     const float4 ba = *reinterpret_cast<const float4 *>(gb_p + 4 * fg), bb = *reinterpret_cast<const float4 *>(gb_p + 32 + 4 * fg);
     const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb_.x, gb_.y, gb_.z, gb_.w}, bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-    for (int r = 0; r < EV_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         float m = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) m += z[r][i];
@@ -95,30 +96,35 @@ __device__ __forceinline__ void ev_gn_silu(float (&z)[EV_RPT][8], const float *g
 // Forward of one 256-row tile.  In: sX = smem + S.x holds the tile's inputs [row][O] (written and synchronised by the
 // caller).  Out: smem + S.out holds [row][S.so] head outputs (head h at columns S.col[h] ..), valid after the caller's
 // next __syncthreads().  Contains one __syncthreads(); every thread of the CTA must call it.
+// RPT = rows per thread: the tile is 32 RPT rows, thread (rg, fg) owns rows RPT rg .. RPT rg + RPT - 1.  8 is the throughput form
+// (64 FMAs per 4 shared-memory loads); the fused rollout of a FEW envs (configs[0]: 32) runs RPT = 1, one row per 8 threads, so
+// that all 8 warps share the 32 rows instead of one warp walking them alone - the step is latency-bound there.  A row's
+// arithmetic (operation order, contraction) does not depend on RPT: the same bits.
+template <int RPT = EV_RPT>
 __device__ __forceinline__ void ev_forward_tile(float *smem, const EvSmem &S, const PolicyLayout &L) {
     const int tid = threadIdx.x, fg = tid & 7, rg = tid >> 3, O = L.O;
     float *sF = smem + S.f, *sO = smem + S.out;
     const float *sX = smem + S.x;
-    float z[EV_RPT][8];
+    float z[RPT][8];
     // ---- trunk: Linear(O, 64, no bias) -> GN -> SiLU -> sF
 #pragma unroll
-    for (int r = 0; r < EV_RPT; ++r)
+    for (int r = 0; r < RPT; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[r][i] = 0.f;
     for (int o = 0; o < O; ++o) {
         const float4 wa = *reinterpret_cast<const float4 *>(smem + S.w0 + o * HID + 4 * fg);
         const float4 wb = *reinterpret_cast<const float4 *>(smem + S.w0 + o * HID + 32 + 4 * fg);
 #pragma unroll
-        for (int r = 0; r < EV_RPT; ++r) {
-            const float xv = sX[(EV_RPT * rg + r) * O + o];
+        for (int r = 0; r < RPT; ++r) {
+            const float xv = sX[(RPT * rg + r) * O + o];
             z[r][0] = fmaf(xv, wa.x, z[r][0]); z[r][1] = fmaf(xv, wa.y, z[r][1]); z[r][2] = fmaf(xv, wa.z, z[r][2]); z[r][3] = fmaf(xv, wa.w, z[r][3]);
             z[r][4] = fmaf(xv, wb.x, z[r][4]); z[r][5] = fmaf(xv, wb.y, z[r][5]); z[r][6] = fmaf(xv, wb.z, z[r][6]); z[r][7] = fmaf(xv, wb.w, z[r][7]);
         }
     }
-    ev_gn_silu(z, smem + S.g0w, smem + S.g0b, fg);
+    ev_gn_silu<RPT>(z, smem + S.g0w, smem + S.g0b, fg);
 #pragma unroll
-    for (int r = 0; r < EV_RPT; ++r) {
-        float *dst = sF + (EV_RPT * rg + r) * HID + 4 * fg;
+    for (int r = 0; r < RPT; ++r) {
+        float *dst = sF + (RPT * rg + r) * HID + 4 * fg;
         *reinterpret_cast<float4 *>(dst) = make_float4(z[r][0], z[r][1], z[r][2], z[r][3]);
         *reinterpret_cast<float4 *>(dst + 32) = make_float4(z[r][4], z[r][5], z[r][6], z[r][7]);
     }
@@ -126,36 +132,36 @@ __device__ __forceinline__ void ev_forward_tile(float *smem, const EvSmem &S, co
     // ---- heads: Linear(64, 64, no bias) -> GN -> SiLU -> Linear(64, out) + bias
     for (int h = 0; h < S.n_heads; ++h) {
 #pragma unroll
-        for (int r = 0; r < EV_RPT; ++r)
+        for (int r = 0; r < RPT; ++r)
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[r][i] = 0.f;
         const float *Wp = smem + S.w1[h] + 4 * fg;
-        const float *Fp = sF + (EV_RPT * rg) * HID;
+        const float *Fp = sF + (RPT * rg) * HID;
 #pragma unroll 2
         for (int k4 = 0; k4 < HID / 4; ++k4) {
-            float4 a[EV_RPT];
+            float4 a[RPT];
 #pragma unroll
-            for (int r = 0; r < EV_RPT; ++r) a[r] = *reinterpret_cast<const float4 *>(Fp + r * HID + 4 * k4);
+            for (int r = 0; r < RPT; ++r) a[r] = *reinterpret_cast<const float4 *>(Fp + r * HID + 4 * k4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const float4 wa = *reinterpret_cast<const float4 *>(Wp + (4 * k4 + kk) * HID);
                 const float4 wb = *reinterpret_cast<const float4 *>(Wp + (4 * k4 + kk) * HID + 32);
 #pragma unroll
-                for (int r = 0; r < EV_RPT; ++r) {
+                for (int r = 0; r < RPT; ++r) {
                     const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
                     z[r][0] = fmaf(av, wa.x, z[r][0]); z[r][1] = fmaf(av, wa.y, z[r][1]); z[r][2] = fmaf(av, wa.z, z[r][2]); z[r][3] = fmaf(av, wa.w, z[r][3]);
                     z[r][4] = fmaf(av, wb.x, z[r][4]); z[r][5] = fmaf(av, wb.y, z[r][5]); z[r][6] = fmaf(av, wb.z, z[r][6]); z[r][7] = fmaf(av, wb.w, z[r][7]);
                 }
             }
         }
-        ev_gn_silu(z, smem + S.gw[h], smem + S.gb[h], fg);
+        ev_gn_silu<RPT>(z, smem + S.gw[h], smem + S.gb[h], fg);
         const int outs = L.head[h].out;
         for (int a = 0; a < outs; ++a) {
             const float4 wa = *reinterpret_cast<const float4 *>(smem + S.w2[h] + a * HID + 4 * fg);
             const float4 wb = *reinterpret_cast<const float4 *>(smem + S.w2[h] + a * HID + 32 + 4 * fg);
             float mine = 0.f;
 #pragma unroll
-            for (int r = 0; r < EV_RPT; ++r) {
+            for (int r = 0; r < RPT; ++r) {
                 float p = ((z[r][0] * wa.x + z[r][1] * wa.y) + (z[r][2] * wa.z + z[r][3] * wa.w)) +
                           ((z[r][4] * wb.x + z[r][5] * wb.y) + (z[r][6] * wb.z + z[r][7] * wb.w));
                 p += __shfl_xor_sync(0xffffffffu, p, 1);
@@ -163,7 +169,7 @@ __device__ __forceinline__ void ev_forward_tile(float *smem, const EvSmem &S, co
                 p += __shfl_xor_sync(0xffffffffu, p, 4);
                 mine = fg == r ? p : mine;
             }
-            sO[(EV_RPT * rg + fg) * S.so + S.col[h] + a] = mine + smem[S.b2[h] + a];   // lane fg keeps row 8 rg + fg
+            if (RPT == 8 || fg < RPT) sO[(RPT * rg + fg) * S.so + S.col[h] + a] = mine + smem[S.b2[h] + a];   // lane fg keeps row RPT rg + fg
         }
     }
 }
