@@ -804,21 +804,27 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
             PRL_REQUIRE(!(buf_logp && ENV::CONT && ENV::A != 1), "prl_rollout_eval: continuous envs with action_dim > 1 are evaluated by prl_policy_evaluate");
             const size_t smem = (size_t)ev_layout(L, buf_logp ? L.n_heads : L.n_heads - 1).total * sizeof(float);
             PRL_REQUIRE(smem <= 227 * 1024, "prl_rollout_eval: %zu B of shared memory needed (> 227 KB)", smem);
-            PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // few envs (at most 32 per CTA slot of the GPU): one row per 8 threads, 32 envs per CTA - see the kernel's header
+            // rows per thread of the forward = envs per CTA / 32 (see the kernel's header):
+            //   1  few envs (at most 32 per CTA slot of the GPU): the step is latency-bound, all 8 warps share the CTA's 32 rows;
+            //   7  when 224-env CTAs fill the CTA slots (2 per SM) more evenly than 256-env ones: 65 536 envs are 256 CTAs of 256 -
+            //      108 SMs carry two of them, 40 carry one - or 293 CTAs of 224, two on every SM with 7/8 of the work each;
+            //   8  otherwise.
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const bool few = E <= 32 * 2 * sms && !getenv("PRL_ROLLOUT_RPT8");   // (the variable: A/B against the throughput form)
-            if (few) {
-                PRL_CUDA(cudaFuncSetAttribute(k_rollout<ENV, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_rollout<ENV, false, 1><<<cdiv(E, 32), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
-                                                                 elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
-                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);
-            } else
-            k_rollout<ENV, false><<<cdiv(E, EV_ROWS), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
-                                                                 elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
-                                                                 lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);
+            const int slots = 2 * sms;
+            auto rounds = [&](int rpt) { return cdiv(cdiv(E, 32 * rpt), slots) * rpt; };   // CTAs an SM slot works through x their size
+            int rpt = E <= 32 * slots ? 1 : rounds(7) < rounds(8) ? 7 : 8;
+            if (const char *ev = getenv("PRL_ROLLOUT_RPT")) rpt = atoi(ev) == 1 || atoi(ev) == 7 ? atoi(ev) : 8;   // (A/B between the forms)
+            auto go = [&](auto kernel, int envs_per_cta) -> int {
+                PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kernel<<<cdiv(E, envs_per_cta), EV_THREADS, smem, st>>>(E, T_cap, params, L, action_scaling, seed, episode, nullptr, state,
+                                                                       elapsed, terminal, buf_states, buf_actions, buf_rewards, buf_dones,
+                                                                       lengths, scores, buf_logp, buf_values, auto_reset_horizon, score_ws);
+                return PRL_OK;
+            };
+            const int rc = rpt == 1 ? go(k_rollout<ENV, false, 1>, 32) : rpt == 7 ? go(k_rollout<ENV, false, 7>, 224) : go(k_rollout<ENV, false, 8>, 256);
+            if (rc != PRL_OK) return rc;
         }
         return check_launch("k_rollout");
     });

@@ -420,17 +420,17 @@ def test_reward_score_is_bit_reproducible(api):
     assert np.frombuffer(got[0][0], np.float64)[0] == pytest.approx(got[0][2], rel=1e-6)   # (the stored rewards are float32 copies)
 
 
-def test_rollout_few_envs_form_stores_the_same_bits(api, monkeypatch):
-    """With at most 32 envs per CTA slot of the GPU the fused worker runs the forward with one row per 8 threads (csrc/rollout.cu,
-    RPT = 1: 32 envs per CTA, the step is latency-bound there) instead of 8 rows per thread; a row's arithmetic does not depend
-    on that: the same transitions, old log-probs, values and returns, bit for bit."""
+def test_rollout_forms_store_the_same_bits(api, monkeypatch):
+    """The fused worker picks how many rows of the forward a thread owns from the env count (csrc/rollout.cu: 1 = 32 envs per CTA
+    when there are few envs and the step is latency-bound, 7 = 224-env CTAs where they fill the GPU's CTA slots more evenly, 8 = 256)
+    - a row's arithmetic does not depend on that: the same transitions, old log-probs, values and returns, bit for bit."""
     A, P, prl = api["AsyncTools"], api["PPO"], api["prl"]
-    got = []
-    for rpt8 in (False, True):
-        if rpt8:
-            monkeypatch.setenv("PRL_ROLLOUT_RPT8", "1")
+    got = {}
+    for form in (None, "8", "7", "1"):
+        if form is None:
+            monkeypatch.delenv("PRL_ROLLOUT_RPT", raising=False)
         else:
-            monkeypatch.delenv("PRL_ROLLOUT_RPT8", raising=False)
+            monkeypatch.setenv("PRL_ROLLOUT_RPT", form)
         for env_id, cont, O, AD in (("CartPole-v1", False, 4, 2), ("Pendulum-v1", True, 3, 1), ("Acrobot-v1", False, 6, 3)):
             t.manual_seed(33)
             ppo = P.PPO(is_continuous=cont, observ_dim=O, action_dim=AD, action_scaling=2.0 if cont else None)
@@ -442,14 +442,14 @@ def test_rollout_few_envs_form_stores_the_same_bits(api, monkeypatch):
             rows = [x.clone() for x in ppo.memory.device_view(O, 1, ppo.device)]
             pre = ppo.memory.evaluated(n, ppo._eval_tag())
             assert pre is not None
-            got.append((env_id, n, int(ap.step_score), float(ap.reward_score), rows + [x.clone() for x in pre if x is not None]))
-    half = len(got) // 2
-    for a, b in zip(got[:half], got[half:]):
-        assert a[:3] == b[:3] and a[3] == pytest.approx(b[3], rel=1e-12)
-        assert len(a[4]) == len(b[4])
-        for x, y in zip(a[4], b[4]):
-            assert t.equal(x, y), a[0]
-    monkeypatch.delenv("PRL_ROLLOUT_RPT8", raising=False)
+            got.setdefault(env_id, []).append((n, int(ap.step_score), float(ap.reward_score), rows + [x.clone() for x in pre if x is not None]))
+    monkeypatch.delenv("PRL_ROLLOUT_RPT", raising=False)
+    for env_id, runs in got.items():
+        for other in runs[1:]:
+            assert other[:2] == runs[0][:2] and other[2] == pytest.approx(runs[0][2], rel=1e-12)
+            assert len(other[3]) == len(runs[0][3])
+            for x, y in zip(runs[0][3], other[3]):
+                assert t.equal(x, y), env_id
 
 
 def test_reference_unittest_call_patterns(api):
