@@ -1268,6 +1268,9 @@ k_reduce_partials_tc(const float *__restrict__ partials, int nblocks, int P, int
 // register-tiled forward of the old-policy evaluation, tiled_mlp.cuh), the clipped-surrogate loss of every row and its gradient
 // with respect to the two heads' outputs - the operation sequence of csrc/update_ppo.cu's continuous branch (PPO.py:219-252,
 // ActorCritic.py:118-146).  dout_mu / dout_ls [b][A]; loss_partials[block][4] = {policy term sum, 0, entropy sum, 0}.
+// RPT: rows of the forward per thread, 32 RPT rows per tile (tiled_mlp.cuh) - 7 where 224-row tiles spread more evenly over the
+// persistent CTAs than 256-row ones (262 144 rows on 296 CTAs: 3.96 tiles of 224 each instead of 3.46 -> 4 tiles of 256).
+template <int RPT>
 __global__ void __launch_bounds__(EV_THREADS, 2)
 k_policy_dout(const float *__restrict__ params, PolicyLayout L, const float *__restrict__ states, const float *__restrict__ actions,
               const float *__restrict__ old_logp, const float *__restrict__ adv, int64_t n, float clip, float inv_count,
@@ -1279,15 +1282,16 @@ k_policy_dout(const float *__restrict__ params, PolicyLayout L, const float *__r
     ev_stage_weights(smem, S, params, L);
     float *sX = smem + S.x;
     const float *sO = smem + S.out;
-    const int64_t ntiles = (n + EV_ROWS - 1) / EV_ROWS;
+    constexpr int ROWS = 32 * RPT;
+    const int64_t ntiles = (n + ROWS - 1) / ROWS;
     double pol_acc = 0.0, ent_acc = 0.0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row0 = tile * EV_ROWS;
-        const int rows = (int)min((int64_t)EV_ROWS, n - row0);
+        const int64_t row0 = tile * ROWS;
+        const int rows = (int)min((int64_t)ROWS, n - row0);
         __syncthreads();
-        for (int i = tid; i < EV_ROWS * O; i += EV_THREADS) sX[i] = i < rows * O ? __ldg(states + row0 * O + i) : 0.f;
+        for (int i = tid; i < ROWS * O; i += EV_THREADS) sX[i] = i < rows * O ? __ldg(states + row0 * O + i) : 0.f;
         __syncthreads();
-        ev_forward_tile(smem, S, L);
+        ev_forward_tile<RPT>(smem, S, L);
         __syncthreads();
         if (tid < rows) {
             const int64_t row = row0 + tid;
@@ -1524,13 +1528,22 @@ int prl_ppo_grad_tc(const float *params, int is_continuous, int obs_dim, int act
     {
         const size_t smem = (size_t)ev_layout(LC, 2).total * sizeof(float);
         PRL_REQUIRE(smem <= 227 * 1024, "%s: pre-pass needs %zu B shared memory", who, smem);
-        PRL_CUDA(cudaFuncSetAttribute(k_policy_dout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int pgrid = 1;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int64_t ntiles = cdiv(b, EV_ROWS);
-        const int pgrid = (int)(ntiles < 2 * sms ? ntiles : (2 * sms < 320 ? 2 * sms : 320));
-        k_policy_dout<<<pgrid, EV_THREADS, smem, st>>>(params, LC, states, actions, old_logp, adv, b, policy_clip, inv_count, dmu, dls, pre_partials);
+        const int slots = 2 * sms < 320 ? 2 * sms : 320;   // (pre_partials holds 320 CTAs' sums)
+        auto rounds = [&](int rpt) { return cdiv(cdiv(b, (int64_t)32 * rpt), (int64_t)slots) * rpt; };   // tiles per CTA x their size
+        const int rpt = rounds(7) < rounds(8) && !getenv("PRL_DOUT_RPT8") ? 7 : 8;
+        const int64_t ntiles = cdiv(b, (int64_t)32 * rpt);
+        pgrid = (int)(ntiles < slots ? ntiles : slots);
+        if (rpt == 7) {
+            PRL_CUDA(cudaFuncSetAttribute(k_policy_dout<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_policy_dout<7><<<pgrid, EV_THREADS, smem, st>>>(params, LC, states, actions, old_logp, adv, b, policy_clip, inv_count, dmu, dls, pre_partials);
+        } else {
+            PRL_CUDA(cudaFuncSetAttribute(k_policy_dout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_policy_dout<8><<<pgrid, EV_THREADS, smem, st>>>(params, LC, states, actions, old_logp, adv, b, policy_clip, inv_count, dmu, dls, pre_partials);
+        }
         if (loss_out) k_add_loss_sums<<<1, 32, 0, st>>>(pre_partials, pgrid, loss_out);
         if (check_launch("k_policy_dout") != PRL_OK) return PRL_ERR_CUDA;
     }
