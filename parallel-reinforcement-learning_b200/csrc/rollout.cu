@@ -812,7 +812,8 @@ int prl_rollout_eval(int env_id, int E, int T_cap, const float *params, float ac
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const int slots = 2 * sms;
+            const int slots = 2 * sms;   // (two resident CTAs per SM: the discrete layouts; the three-head continuous layout of
+                                         //  121 KB fits once, where 7 and 8 rows tie at the BASELINE sizes - a model, not a measurement)
             auto rounds = [&](int rpt) { return cdiv(cdiv(E, 32 * rpt), slots) * rpt; };   // CTAs an SM slot works through x their size
             int rpt = E <= 32 * slots ? 1 : rounds(7) < rounds(8) ? 7 : 8;
             if (const char *ev = getenv("PRL_ROLLOUT_RPT")) rpt = atoi(ev) == 1 || atoi(ev) == 7 ? atoi(ev) : 8;   // (A/B between the forms)
